@@ -1,0 +1,33 @@
+// Internal (non-ABI) declarations shared between the translation units of libgnca.so.
+#pragma once
+#include <stddef.h>
+#include "gnca_common.cuh"
+
+namespace gnca {
+
+struct FwdWorkspace {
+  double* partials;   // [B][nchunks][2]
+  float* rowsum;      // [B][C][H]
+  float* attn_w;      // [B][MAX_K]
+  float* absmean;     // [B][H][W]
+  size_t bytes;
+};
+
+FwdWorkspace carve_fwd_workspace(void* base, const gnca_model& m, int B, int H, int W);
+void fill_step_args(StepArgs& a, const gnca_model& m, int B, int H, int W);
+int set_host_offsets(StepArgs& a, const int32_t* offsets_host, int k);
+int dispatch_step_fwd(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const FwdWorkspace& ws,
+                      float* attn_out, cudaStream_t st);
+// recompute only the masked pre-norm update u (+ statistics) of a step: the forward half the backward needs
+int dispatch_step_recompute(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a,
+                            const FwdWorkspace& ws, cudaStream_t st);
+
+size_t bwd_workspace_bytes(const gnca_model& m, int B, int H, int W);
+// Backward of one step.  `a` describes the step (x_in, u, schedule...).  Weight-gradient partials live in the
+// workspace: zero_partials clears them first, reduce_partials folds them into gparams at the end (a rollout
+// clears at its first step and reduces after its last).
+int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, const StepArgs& a, const float* stats,
+                 const float* gout, float* gx, float* gparams, void* bwd_ws, bool zero_partials, bool reduce_partials,
+                 cudaStream_t st);
+
+}  // namespace gnca

@@ -1,0 +1,180 @@
+// Rollout entry points (the loop of train_graph_augmented_nca.py:302-324 as ONE call).
+//   impl 1 (streaming): per-step kernels of gnca_fwd.cu / gnca_bwd.cu driven by a device-resident schedule --
+//                       no host synchronisation inside the loop, so the whole call can sit in a CUDA graph.
+//   impl 2 (resident):  cluster kernel of gnca_resident.cu (state stays in shared memory across steps).
+// BPTT stores only x_t (x_hist); u, the hidden layer, masks and the message are recomputed in the backward.
+#include "gnca_common.cuh"
+#include "gnca_internal.h"
+
+namespace gnca {
+
+__global__ void k_mul_inplace(size_t n, float* __restrict__ x, const float* __restrict__ m) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= m[i];
+}
+
+struct RolloutWorkspace {
+  float* ping;     // [B][C][H][W]
+  float* pong;
+  float* u;        // [B][C][H][W]
+  float* stats;    // [B][2]
+  float* g_a;      // gradient ping-pong
+  float* g_b;
+  char* step_ws;   // forward + backward per-step workspace
+  size_t step_bytes;
+  size_t bytes;
+};
+
+static inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
+
+static RolloutWorkspace carve_rollout(void* base, const gnca_model& m, int B, int H, int W) {
+  RolloutWorkspace r;
+  const size_t N = (size_t)B * m.C * H * W * sizeof(float);
+  char* p = reinterpret_cast<char*>(base);
+  size_t o = 0;
+  r.ping = reinterpret_cast<float*>(p + o); o = al(o + N);
+  r.pong = reinterpret_cast<float*>(p + o); o = al(o + N);
+  r.u = reinterpret_cast<float*>(p + o); o = al(o + N);
+  r.g_a = reinterpret_cast<float*>(p + o); o = al(o + N);
+  r.g_b = reinterpret_cast<float*>(p + o); o = al(o + N);
+  r.stats = reinterpret_cast<float*>(p + o); o = al(o + (size_t)B * 2 * sizeof(float));
+  r.step_ws = p + o;
+  r.step_bytes = carve_fwd_workspace(nullptr, m, B, H, W).bytes + bwd_workspace_bytes(m, B, H, W);
+  o = al(o + r.step_bytes);
+  r.bytes = o;
+  return r;
+}
+
+static void schedule_to_args(StepArgs& a, const gnca_schedule& s, int t, int B, int H, int W) {
+  a.t = t;
+  a.k = s.k;
+  a.fire_rate_dev = s.fire_rate;
+  a.message_gain_dev = s.message_gain;
+  a.offsets_dev = s.offsets;
+  a.steps = s.steps;
+  a.fire_u = s.fire_u ? s.fire_u + (size_t)t * B * H * W : nullptr;
+  a.philox_seed = s.philox_seed;
+  a.philox_offset = s.philox_offset;
+}
+
+}  // namespace gnca
+
+using namespace gnca;
+
+extern "C" {
+
+size_t gnca_rollout_workspace_bytes(const gnca_model* m, int B, int H, int W, int T) {
+  (void)T;
+  if (!m || B <= 0 || H <= 0 || W <= 0) return 0;
+  return carve_rollout(nullptr, *m, B, H, W).bytes;
+}
+
+int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const gnca_schedule* sched,
+                     const float* x0_dev, float* xT_dev, float* x_hist_dev, float* stats_hist_dev, void* workspace_dev,
+                     size_t workspace_bytes, int impl, void* stream) {
+  if (!m || !packed_dev || !sched || !x0_dev || !xT_dev || !workspace_dev) return GNCA_ERR_ARG;
+  if (B <= 0 || H <= 0 || W <= 0 || sched->T < 0) return GNCA_ERR_ARG;
+  if (!model_supported(*m)) return GNCA_ERR_UNSUPPORTED;
+  const bool graph = (m->flags & GNCA_F_GRAPH) != 0;
+  if (sched->T > 0 && (!sched->fire_rate || (graph && !sched->message_gain))) return GNCA_ERR_ARG;
+  if (graph && sched->k > 0 && !sched->offsets) return GNCA_ERR_ARG;
+  if (sched->k < 0 || sched->k > GNCA_MAX_K) return GNCA_ERR_UNSUPPORTED;
+  if (impl == 2) return GNCA_ERR_UNSUPPORTED;   // TODO(resident)
+  cudaStream_t st = (cudaStream_t)stream;
+  RolloutWorkspace r = carve_rollout(workspace_dev, *m, B, H, W);
+  if (r.bytes > workspace_bytes) return GNCA_ERR_WORKSPACE;
+  const size_t N = (size_t)B * m->C * H * W;
+  const Packed P = make_packed(m->C, m->hidden, m->d_model, graph);
+  FwdWorkspace fws = carve_fwd_workspace(r.step_ws, *m, B, H, W);
+  const int T = sched->T;
+
+  // where x_t lives: x_hist slices when a history is requested, else ping/pong (x_T straight into xT_dev)
+  auto x_at = [&](int t) -> float* {
+    if (x_hist_dev) return x_hist_dev + (size_t)t * N;
+    if (t == T) return xT_dev;
+    return (t & 1) ? r.pong : r.ping;
+  };
+  GNCA_CHECK_CUDA(cudaMemcpyAsync(x_at(0), x0_dev, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int t = 0; t < T; ++t) {
+    if (sched->damage && t == sched->damage_step) {
+      k_mul_inplace<<<(int)((N + 1023) / 1024 < 2368 ? (N + 1023) / 1024 : 2368), 256, 0, st>>>(N, x_at(t), sched->damage);
+      GNCA_LAUNCH_CHECK();
+    }
+    StepArgs a;
+    fill_step_args(a, *m, B, H, W);
+    schedule_to_args(a, *sched, t, B, H, W);
+    if (!graph) a.k = 0;
+    a.x_in = x_at(t);
+    a.x_out = x_at(t + 1);
+    a.u = r.u;
+    a.stats = stats_hist_dev ? stats_hist_dev + (size_t)t * B * 2 : r.stats;
+    int rc = dispatch_step_fwd(*m, P, packed_dev, a, fws, nullptr, st);
+    if (rc) return rc;
+  }
+  if (x_hist_dev || T == 0)
+    GNCA_CHECK_CUDA(cudaMemcpyAsync(xT_dev, x_at(T), N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const gnca_schedule* sched,
+                     const float* x_hist_dev, const float* stats_hist_dev, const float* gT_dev, float* g0_dev,
+                     float* gparams_dev, void* workspace_dev, size_t workspace_bytes, int impl, void* stream) {
+  if (!m || !packed_dev || !sched || !x_hist_dev || !gT_dev || !g0_dev || !gparams_dev || !workspace_dev)
+    return GNCA_ERR_ARG;
+  if (B <= 0 || H <= 0 || W <= 0 || sched->T < 0) return GNCA_ERR_ARG;
+  if (!model_supported(*m)) return GNCA_ERR_UNSUPPORTED;
+  if (impl == 2) return GNCA_ERR_UNSUPPORTED;   // TODO(resident)
+  (void)stats_hist_dev;   // statistics are recomputed together with u
+  const bool graph = (m->flags & GNCA_F_GRAPH) != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  RolloutWorkspace r = carve_rollout(workspace_dev, *m, B, H, W);
+  if (r.bytes > workspace_bytes) return GNCA_ERR_WORKSPACE;
+  const size_t N = (size_t)B * m->C * H * W;
+  const Packed P = make_packed(m->C, m->hidden, m->d_model, graph);
+  FwdWorkspace fws = carve_fwd_workspace(r.step_ws, *m, B, H, W);
+  char* bws = r.step_ws + fws.bytes;
+  const int T = sched->T;
+  if (T == 0) {
+    GNCA_CHECK_CUDA(cudaMemcpyAsync(g0_dev, gT_dev, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  const float* gcur = gT_dev;
+  for (int t = T - 1; t >= 0; --t) {
+    StepArgs a;
+    fill_step_args(a, *m, B, H, W);
+    schedule_to_args(a, *sched, t, B, H, W);
+    if (!graph) a.k = 0;
+    a.x_in = x_hist_dev + (size_t)t * N;
+    a.x_out = nullptr;
+    a.u = r.u;
+    a.stats = r.stats;
+    int rc = dispatch_step_recompute(*m, P, packed_dev, a, fws, st);
+    if (rc) return rc;
+    float* gnext = (t == 0) ? g0_dev : (((T - 1 - t) & 1) ? r.g_b : r.g_a);
+    rc = run_step_bwd(*m, P, packed_dev, a, r.stats, gcur, gnext, gparams_dev, bws, t == T - 1, t == 0, st);
+    if (rc) return rc;
+    if (sched->damage && t == sched->damage_step) {
+      k_mul_inplace<<<(int)((N + 1023) / 1024 < 2368 ? (N + 1023) / 1024 : 2368), 256, 0, st>>>(N, gnext, sched->damage);
+      GNCA_LAUNCH_CHECK();
+    }
+    gcur = gnext;
+  }
+  return 0;
+}
+
+int gnca_graph_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const float* x_dev,
+                   const int32_t* offsets_host, int k, float* msg_dev, float* attn_dev, void* workspace_dev,
+                   size_t workspace_bytes, void* stream) {
+  (void)m; (void)packed_dev; (void)B; (void)H; (void)W; (void)x_dev; (void)offsets_host; (void)k; (void)msg_dev;
+  (void)attn_dev; (void)workspace_dev; (void)workspace_bytes; (void)stream;
+  return GNCA_ERR_UNSUPPORTED;
+}
+
+int gnca_graph_bwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const float* x_dev,
+                   const int32_t* offsets_host, int k, const float* gmsg_dev, float* gx_dev, float* gparams_dev,
+                   void* workspace_dev, size_t workspace_bytes, void* stream) {
+  (void)m; (void)packed_dev; (void)B; (void)H; (void)W; (void)x_dev; (void)offsets_host; (void)k; (void)gmsg_dev;
+  (void)gx_dev; (void)gparams_dev; (void)workspace_dev; (void)workspace_bytes; (void)stream;
+  return GNCA_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

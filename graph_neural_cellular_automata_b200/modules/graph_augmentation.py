@@ -1,0 +1,57 @@
+"""Drop-in for the reference's `modules/graph_augmentation.py` (GraphAugmentation, :8-169).
+
+Keeps the constructor, the attributes the reference's scripts read (`offsets`, `num_neighbors`,
+`zero_padded_shift`, `alive_to_alive`, `scaling`, `query_proj`, `key_proj`, `msg_proj`, `gate_mlp`), the
+state-dict keys, and the RNG side effect (exactly one `random.sample(self.offsets, k)` per forward).
+The arithmetic runs in libgnca.so: the k shifted copies of K / M / A_send the reference materialises are
+replaced by in-place neighbour reads (see csrc/gnca_common.cuh: gather_senders).
+"""
+from __future__ import annotations
+
+import math
+import random
+from typing import List, Tuple
+
+import torch
+import torch.nn as nn
+
+
+def build_offsets(radius: int) -> List[Tuple[int, int]]:
+    """Mid-range ring: Chebyshev distance in (1, radius], dy-major / dx-minor (graph_augmentation.py:73-83)."""
+    span = range(-radius, radius + 1)
+    return [(dy, dx) for dy in span for dx in span if max(abs(dy), abs(dx)) >= 2]
+
+
+class GraphAugmentation(nn.Module):
+    def __init__(self, n_channels: int, d_model: int = 16, attention_radius: int = 4, num_neighbors: int = 8,
+                 gating_hidden: int = 32, *, alive_to_alive: bool = True, zero_padded_shift: bool = True,
+                 alpha_thr: float = 0.1):
+        super().__init__()
+        self.n_channels = n_channels
+        self.d_model = d_model
+        self.attention_radius = attention_radius
+        self.num_neighbors = num_neighbors
+        self.alive_to_alive = bool(alive_to_alive)
+        self.zero_padded_shift = bool(zero_padded_shift)
+        self.alpha_thr = float(alpha_thr)
+        # parameter containers, created in the reference's order (:55-68) so seeded init is identical
+        self.query_proj = nn.Conv2d(n_channels, d_model, 1)
+        self.key_proj = nn.Conv2d(n_channels, d_model, 1)
+        self.msg_proj = nn.Conv2d(n_channels, n_channels, 1)
+        self.scaling = nn.Parameter(torch.tensor(math.sqrt(d_model), dtype=torch.float32))
+        # never evaluated by the reference's forward ("implemented but disabled"); kept for checkpoint keys
+        self.gate_mlp = nn.Sequential(nn.Conv2d(2 * n_channels, gating_hidden, 1), nn.ReLU(inplace=False),
+                                      nn.Conv2d(gating_hidden, n_channels, 1), nn.Sigmoid())
+        self.offsets = build_offsets(attention_radius)
+
+    _build_offsets = staticmethod(build_offsets)
+
+    def draw_offsets(self) -> List[Tuple[int, int]]:
+        """The per-forward draw of graph_augmentation.py:120-121 (Python global RNG, also at message_gain 0)."""
+        k = min(self.num_neighbors, len(self.offsets))
+        return random.sample(self.offsets, k) if k > 0 else []
+
+    def forward(self, x: torch.Tensor, return_attention_map: bool = False):
+        from .. import graph_ops
+        chosen = self.draw_offsets()
+        return graph_ops.graph_message(self, x, chosen, return_attention_map)

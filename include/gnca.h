@@ -1,0 +1,180 @@
+/*
+ * gnca.h -- C ABI of libgnca.so: the B200 (sm_100a) graph-NCA step / rollout kernels.
+ *
+ * This is the drop-in boundary for the hot path of Psylocibe23/Graph_Neural_Cellular_Automata.  The
+ * reference has no FFI layer (it is pure PyTorch); what these entry points replace are the bodies of
+ *
+ *   FixedSobelPerception.forward      src/modules/perception.py:21-26            -> gnca_perception_fwd/_bwd
+ *   NeuralCA._alive_mask              src/modules/nca.py:55-62                   -> gnca_alive_mask
+ *   GraphAugmentation.forward         src/modules/graph_augmentation.py:104-169  -> gnca_graph_fwd/_bwd
+ *   NeuralCA.forward                  src/modules/nca.py:64-105                  -> gnca_step_fwd/_bwd (GNCA_F_GRAPH clear)
+ *   NeuralCAGraph.forward             src/modules/ncagraph.py:106-168            -> gnca_step_fwd/_bwd (GNCA_F_GRAPH set)
+ *   the rollout loop                  src/training/train_graph_augmented_nca.py:302-324 -> gnca_rollout_fwd/_bwd
+ *   loss_premult_rgba (+ its grad)    src/training/train_graph_augmented_nca.py:52-61,337-339 -> gnca_loss_premult_rgba
+ *   grad normalise + Adam             src/training/train_graph_augmented_nca.py:370-375 -> gnca_normalize_adam
+ *   multiplicative damage             src/utils/damage.py:16-98                  -> gnca_apply_mask
+ *
+ * Conventions
+ *   - every pointer named *_dev / documented "device" is a CUDA device pointer; tensors are fp32,
+ *     contiguous NCHW exactly as the reference's modules take them;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 = ok, >0 = a cudaError_t, <0 = one of GNCA_ERR_*.  Nothing throws;
+ *   - no call ever falls back to the host: an unsupported configuration returns GNCA_ERR_UNSUPPORTED.
+ *
+ * Parameters travel as ONE flat fp32 device buffer in the canonical order of gnca_param_layout()
+ * (same orientation as the reference's state_dict tensors).  gnca_pack_weights() derives the
+ * kernel-side buffer (adds transposed copies for the forward MLP); gradients come back in the canonical
+ * layout.
+ */
+#ifndef GNCA_H_
+#define GNCA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNCA_VERSION 101
+
+#define GNCA_ERR_ARG (-1)         /* null pointer / bad size */
+#define GNCA_ERR_UNSUPPORTED (-2) /* shape or flag combination without a kernel */
+#define GNCA_ERR_WORKSPACE (-3)   /* workspace too small */
+
+#define GNCA_F_GRAPH 1u          /* NeuralCAGraph (else classic NeuralCA) */
+#define GNCA_F_TORUS 2u          /* graph shift = torch.roll (graph_zero_padded_shift=False) */
+#define GNCA_F_HIDDEN_ONLY 4u    /* ncagraph.py:98-101 */
+#define GNCA_F_ALIVE_TO_ALIVE 8u /* graph_augmentation.py:116-117,130-133 */
+#define GNCA_F_GROUPNORM 16u     /* use_groupnorm */
+
+#define GNCA_MAX_K 64 /* chosen offsets per step */
+
+typedef struct gnca_model {
+  int32_t C;       /* n_channels: 4, 8, 16 or 32 */
+  int32_t hidden;  /* update_hidden, multiple of 4, <= 256 */
+  int32_t d_model; /* graph_d_model (used by the zero-padded-shift attention only), <= 64 */
+  uint32_t flags;  /* GNCA_F_* */
+  float update_gain;
+  float alpha_thr;       /* model.alpha_thr  (pre / post alive) */
+  float graph_alpha_thr; /* model.graph.alpha_thr (sender alive) */
+  float gn_eps;          /* 1e-3 in the reference */
+} gnca_model;
+
+/* offsets (in floats) of each tensor inside the canonical flat parameter / gradient buffer; -1 = absent */
+typedef struct gnca_layout {
+  int64_t w1, b1, w2;   /* update_net.0.weight [hidden,3C], update_net.0.bias [hidden], update_net.2.weight [C,hidden] */
+  int64_t gamma, beta;  /* norm.weight, norm.bias [C] (present even when GroupNorm is off) */
+  int64_t wm, bm;       /* graph.msg_proj [C,C],[C] */
+  int64_t wq, bq;       /* graph.query_proj [d,C],[d] */
+  int64_t wk, bk;       /* graph.key_proj [d,C],[d] */
+  int64_t scaling;      /* graph.scaling [1] */
+  int64_t total;        /* floats in the canonical buffer */
+  int64_t packed_total; /* floats in the packed (kernel-side) buffer */
+} gnca_layout;
+
+/* Per-step schedule of a rollout; every array lives on the DEVICE. */
+typedef struct gnca_schedule {
+  int32_t T;                  /* steps */
+  int32_t k;                  /* offsets per step (0 for classic) */
+  const float* fire_rate;     /* [T]   fire_rate of step t (>= 1 -> no mask) */
+  const float* message_gain;  /* [T]   model.message_gain at step t (0 -> message skipped) */
+  const int8_t* offsets;      /* [T][k][2] (dy,dx) drawn by random.sample at step t */
+  const int32_t* steps;       /* [B] per-sample step counts (sample b advances while steps[b] > t) or NULL */
+  const float* fire_u;        /* [T][B][H][W] uniforms (the reference's torch.rand draws) or NULL */
+  uint64_t philox_seed;       /* used when fire_u == NULL: in-kernel Philox4x32-10 uniforms */
+  uint64_t philox_offset;
+  const float* damage;        /* [B][C][H][W] multiplicative mask applied to x BEFORE step damage_step, or NULL */
+  int32_t damage_step;
+} gnca_schedule;
+
+int gnca_version(void);
+const char* gnca_error_string(int code);
+
+int gnca_param_layout(const gnca_model* m, gnca_layout* out);
+/* canonical flat params -> packed kernel-side buffer (packed_total floats) */
+int gnca_pack_weights(const gnca_model* m, const float* params_dev, float* packed_dev, void* stream);
+
+/* ------------------------------------------------------------------ single operators ------- */
+/* perception.py:21-26 : x [B,C,H,W] -> y [B,3C,H,W] = [identity | sobel_x | sobel_y], zero halo */
+int gnca_perception_fwd(int B, int C, int H, int W, const float* x_dev, float* y_dev, void* stream);
+/* transpose: gy [B,3C,H,W] -> gx [B,C,H,W] */
+int gnca_perception_bwd(int B, int C, int H, int W, const float* gy_dev, float* gx_dev, void* stream);
+/* nca.py:55-62 : (maxpool3x3(x[:,3]) > thr) as float [B,1,H,W] */
+int gnca_alive_mask(int B, int C, int H, int W, const float* x_dev, float thr, float* mask_dev, void* stream);
+
+/* ------------------------------------------------------------------ one CA step ------------- */
+size_t gnca_step_workspace_bytes(const gnca_model* m, int B, int H, int W);
+
+/*
+ * x_out = step(x_in).  fire_u_dev: [B,H,W] uniforms or NULL (required iff fire_rate < 1).
+ * offsets_host: k (dy,dx) pairs, HOST memory (the module's random.sample result); k may be 0.
+ * u_dev [B,C,H,W] and stats_dev [B,2] receive the masked pre-norm update and (mean, rstd): scratch for
+ * inference, saved tensors for gnca_step_bwd.  attn_dev: optional [B,H,W] normalised attention map.
+ */
+int gnca_step_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W,
+                  const float* x_in_dev, float* x_out_dev,
+                  const float* fire_u_dev, float fire_rate,
+                  const int32_t* offsets_host, int k, float message_gain,
+                  float* u_dev, float* stats_dev, float* attn_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * Backward of gnca_step_fwd.  gx_dev = dL/dx_in (overwritten); gparams_dev (canonical layout) is
+ * ACCUMULATED into (+=) so a rollout can sum over steps; zero it first for a single step.
+ */
+int gnca_step_bwd(const gnca_model* m, const float* packed_dev, int B, int H, int W,
+                  const float* x_in_dev, const float* fire_u_dev, float fire_rate,
+                  const int32_t* offsets_host, int k, float message_gain,
+                  const float* u_dev, const float* stats_dev,
+                  const float* gout_dev, float* gx_dev, float* gparams_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* GraphAugmentation.forward alone: m [B,C,H,W] (+ optional attn [B,H,W]); bwd accumulates into gparams */
+int gnca_graph_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const float* x_dev,
+                   const int32_t* offsets_host, int k, float* msg_dev, float* attn_dev,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
+int gnca_graph_bwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const float* x_dev,
+                   const int32_t* offsets_host, int k, const float* gmsg_dev, float* gx_dev,
+                   float* gparams_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ rollout ----------------- */
+size_t gnca_rollout_workspace_bytes(const gnca_model* m, int B, int H, int W, int T);
+
+/*
+ * T steps in one call.  x_hist_dev: NULL for inference, else [T+1][B][C][H][W] receives x_0..x_T
+ * (what the backward recomputes from; x_T is also written to xT_dev).  stats_hist_dev: [T][B][2] or NULL.
+ * `impl`: 0 = auto, 1 = streaming per-step kernels (any shape), 2 = cluster-resident kernel
+ * (state lives in shared memory across all T steps; needs the sample to fit, torus or classic).
+ */
+int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W,
+                     const gnca_schedule* sched, const float* x0_dev, float* xT_dev,
+                     float* x_hist_dev, float* stats_hist_dev,
+                     void* workspace_dev, size_t workspace_bytes, int impl, void* stream);
+
+/* BPTT: given gT = dL/dx_T and the x_hist of the forward, produce g0 = dL/dx_0 and ACCUMULATE gparams. */
+int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H, int W,
+                     const gnca_schedule* sched, const float* x_hist_dev, const float* stats_hist_dev,
+                     const float* gT_dev, float* g0_dev, float* gparams_dev,
+                     void* workspace_dev, size_t workspace_bytes, int impl, void* stream);
+
+/* ------------------------------------------------------------------ training glue ----------- */
+/* per_sample[b] = mean_{4HW}([rgb*a, a] - target)^2 ; gx (optional) = d(scale * sum_b per_sample[b])/dx, [B,C,H,W] */
+int gnca_loss_premult_rgba(int B, int C, int H, int W, const float* x_dev, const float* target_dev /*[4,H,W]*/,
+                           float* per_sample_dev, float* gx_dev, float scale, void* stream);
+/*
+ * For each of n_seg parameter tensors (seg_off[i]..seg_off[i+1] in the flat buffers, host array of n_seg+1):
+ * g /= (||g||_2 + 1e-8) unless seg_has_grad[i]==0 (skipped like a None grad), then torch.optim.Adam
+ * with coupled L2 weight decay.  step is 1-based.
+ */
+int gnca_normalize_adam(float* params_dev, float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                        const int64_t* seg_off_host, const int32_t* seg_has_grad_host, int n_seg,
+                        int normalize, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        int64_t step, void* stream);
+/* x *= mask (damage.py as multiplicative masks); mask [B,C,H,W] */
+int gnca_apply_mask(int64_t n, float* x_dev, const float* mask_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNCA_H_ */

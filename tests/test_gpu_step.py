@@ -1,0 +1,220 @@
+"""GPU parity of the CUDA step (through the module API -> ctypes -> C ABI) against the CPU oracle and the golden
+fixtures recorded from the reference.  Tolerances: state 1e-5 relative (max |d| / max(|ref|, 0.1) and rel-Frobenius),
+masks bit-exact, gradients 1e-4 rel-Frobenius per tensor (torus Q/K/scaling: absolute <= 1e-8)."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, load_params, max_rel, rel_err
+from oracle import nca_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import graph_neural_cellular_automata_b200 as G
+    from graph_neural_cellular_automata_b200 import functional as GF
+
+DEV = "cuda"
+T32 = lambda a: torch.from_numpy(np.asarray(a)).float()
+tup = lambda ch: [tuple(int(v) for v in o) for o in ch]
+
+
+def graph_model(torus=True, gain=0.25):
+    m = G.NeuralCAGraph(16, update_hidden=128, img_size=40, update_gain=0.05, alpha_thr=0.12, message_gain=gain,
+                        hidden_only=True, graph_zero_padded_shift=not torus)
+    missing, unexpected = m.load_state_dict(load_params("weights_graph_ep960.npz"), strict=False)
+    assert not missing and not unexpected
+    return m.to(DEV)
+
+
+def classic_model():
+    m = G.NeuralCA(16, update_hidden=128, img_size=40, update_gain=0.1, alpha_thr=0.1)
+    missing, unexpected = m.load_state_dict(load_params("weights_classic_ep990.npz"), strict=False)
+    assert not missing and not unexpected
+    return m.to(DEV)
+
+
+def ocfg(torus=True, gain=0.25):
+    return O.StepConfig(update_gain=0.05, alpha_thr=0.12, graph=True, message_gain=gain, hidden_only=True,
+                        zero_padded_shift=not torus)
+
+
+def test_library_loaded():
+    from graph_neural_cellular_automata_b200 import _lib
+    lib = _lib.load()
+    assert lib.gnca_version() == _lib.GNCA_VERSION
+    assert any("libgnca.so" in l for l in open("/proc/self/maps"))
+
+
+def test_perception_and_alive():
+    f = load_golden("facts.npz")
+    x = T32(f["perc_in"]).to(DEV)
+    y = G.FixedSobelPerception(16).to(DEV)(x)
+    assert rel_err(y.cpu(), f["perc_out"]) < 1e-6
+    # backward = transpose
+    xr = x.clone().requires_grad_(True)
+    g = torch.randn_like(y)
+    GF.perception(xr).backward(g)
+    xo = x.cpu().clone().requires_grad_(True)
+    O.perception(xo).backward(g.cpu())
+    assert rel_err(xr.grad.cpu(), xo.grad) < 1e-6
+    a = GF.alive_mask(T32(f["alive_in"]).to(DEV), 0.12)
+    assert torch.equal(a.cpu(), T32(f["alive_out"]))
+
+
+@pytest.mark.parametrize("name,torus", [("torus", True), ("zeropad", False)])
+def test_graph_single_step_golden(name, torus):
+    g = load_golden(f"graph_{name}_step.npz")
+    m = graph_model(torus)
+    x = T32(g["x_in"]).to(DEV)
+    with torch.no_grad():
+        out, attn = m.step(x, float(g["fire_rate"]), fire_u=T32(g["fire_u"]).to(DEV), chosen=tup(g["chosen"]),
+                           return_attention=True)
+        full = m.step(x, 1.0, chosen=tup(g["chosen_full"]))
+    assert max_rel(out.cpu(), g["x_out"]) < 1e-5 and rel_err(out.cpu(), g["x_out"]) < 1e-5
+    assert max_rel(attn.cpu(), g["attn"], floor=1e-2) < 1e-4
+    assert max_rel(full.cpu(), g["x_out_full"]) < 1e-5
+    assert torch.equal(GF.alive_mask(out, 0.12).cpu(), O.alive_mask(T32(g["x_out"]), 0.12))
+
+
+def _rollout_steps(m, g, T, graph=True, check_every=1):
+    x = T32(g["x_0"]).to(DEV)
+    worst = 0.0
+    with torch.no_grad():
+        for t in range(T):
+            ch = tup(g["chosen"][t]) if graph else None
+            x = m.step(x, float(g["fire_rate"]), fire_u=T32(g["fire_u"][t]).to(DEV), chosen=ch)
+            if f"x_{t + 1}" in g:
+                ref = T32(g[f"x_{t + 1}"])
+                worst = max(worst, rel_err(x.cpu(), ref))
+                assert rel_err(x.cpu(), ref) < 1e-5, (t, rel_err(x.cpu(), ref))
+                assert torch.equal(GF.alive_mask(x, 0.12).cpu(), O.alive_mask(ref, 0.12)), t
+    return x
+
+
+def test_graph_torus_rollout_golden():
+    _rollout_steps(graph_model(True), load_golden("graph_torus_rollout.npz"), 48)
+
+
+def test_graph_zeropad_rollout_golden():
+    _rollout_steps(graph_model(False), load_golden("graph_zeropad_rollout.npz"), 12)
+
+
+def test_classic_rollout_golden():
+    _rollout_steps(classic_model(), load_golden("classic_rollout.npz"), 48, graph=False)
+
+
+def _grad_case(fname, m, torus_graph):
+    g = load_golden(fname)
+    T = len(g["gains"])
+    x0 = T32(g["x0"]).to(DEV).requires_grad_(True)
+    steps = torch.from_numpy(g["steps"]).long() if "steps" in g else None
+    target = T32(np.load(os.path.join(GOLDEN, "target_gecko_surrogate.npy"))).to(DEV)
+    state = x0
+    for t in range(T):
+        fu = T32(g["fire_u"][t]).to(DEV)
+        ch = tup(g["chosen"][t]) if g["chosen"].size else None
+        if steps is None:
+            state = m.step(state, float(g["fire_rates"][t]), fire_u=fu, chosen=ch, message_gain=float(g["gains"][t]))
+        else:
+            mask = (steps > t).to(DEV)
+            if not bool(mask.any()):
+                continue
+            new = m.step(state[mask], float(g["fire_rates"][t]), fire_u=fu[mask], chosen=ch,
+                         message_gain=float(g["gains"][t]))
+            state = state.clone()
+            state[mask] = new
+    pred = state[:, :4]
+    rgba = torch.cat([pred[:, :3] * pred[:, 3:4], pred[:, 3:4]], 1)
+    per = ((rgba - target.unsqueeze(0)) ** 2).mean(dim=(1, 2, 3))
+    per.mean().backward()
+    assert rel_err(state.detach().cpu(), g["x_T"]) < 1e-5
+    assert rel_err(per.detach().cpu(), g["per_sample"]) < 1e-5
+    assert rel_err(x0.grad.cpu(), g["grad_x0"]) < 1e-4, rel_err(x0.grad.cpu(), g["grad_x0"])
+    named = dict(m.named_parameters())
+    for k, v in g.items():
+        if not k.startswith("grad:"):
+            continue
+        name = k[5:]
+        p = named[name]
+        if v.size == 0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        ours = p.grad if p.grad is not None else torch.zeros_like(p)
+        if torus_graph and any(s in name for s in ("query_proj", "key_proj", "scaling")):
+            assert float(ours.abs().max()) <= 1e-8, name          # exact zero by construction (uniform softmax)
+        else:
+            assert rel_err(ours.cpu(), v) < 1e-4, (name, rel_err(ours.cpu(), v))
+
+
+def test_grads_graph_torus():
+    _grad_case("graph_torus_grads.npz", graph_model(True), True)
+
+
+def test_grads_graph_torus_ragged():
+    _grad_case("graph_torus_grads_ragged.npz", graph_model(True), True)
+
+
+def test_grads_classic():
+    _grad_case("classic_grads.npz", classic_model(), False)
+
+
+def test_dropin_rng_streams():
+    """forward() consumes random.sample then torch.rand exactly like the reference."""
+    m = graph_model(True)
+    x = T32(load_golden("graph_torus_step.npz")["x_in"]).to(DEV)
+    torch.manual_seed(123); random.seed(123)
+    with torch.no_grad():
+        y = m(x, fire_rate=0.5)
+    after_py, after_t = random.random(), torch.rand(1, device=DEV)
+    torch.manual_seed(123); random.seed(123)
+    chosen = random.sample(m.graph.offsets, 8)
+    fu = torch.rand(2, 1, 40, 40, device=DEV)
+    assert random.random() == after_py and torch.equal(torch.rand(1, device=DEV), after_t)
+    ref = O.nca_step(x.cpu(), load_params("weights_graph_ep960.npz"), ocfg(True), 0.5, fu.cpu(), chosen)
+    assert max_rel(y.cpu(), ref) < 1e-5
+    # message_gain == 0 still draws offsets; fire_rate == 1 draws no uniforms
+    m.message_gain = 0.0
+    random.seed(5); torch.manual_seed(5)
+    with torch.no_grad():
+        m(x, fire_rate=1.0)
+    r1 = random.random(); t1 = torch.rand(1, device=DEV)
+    random.seed(5); torch.manual_seed(5)
+    random.sample(m.graph.offsets, 8)
+    assert random.random() == r1 and torch.equal(torch.rand(1, device=DEV), t1)
+
+
+def test_small_shapes_and_channels():
+    """C in {4,8,32}, odd grids, zero-pad and torus, vs the oracle with random weights."""
+    torch.manual_seed(0); random.seed(0)
+    for C, Hh, Ww, hid in ((4, 9, 7, 32), (8, 17, 33, 64), (32, 20, 24, 128)):
+        for torus in (True, False):
+            m = G.NeuralCAGraph(C, update_hidden=hid, img_size=Hh, update_gain=0.1, alpha_thr=0.1, message_gain=0.3,
+                                hidden_only=True, graph_attention_radius=3, graph_num_neighbors=5,
+                                graph_zero_padded_shift=not torus)
+            with torch.no_grad():
+                m.update_net[2].weight.normal_(0, 0.05)
+                m.norm.weight.uniform_(0.5, 1.5); m.norm.bias.normal_(0, 0.1)
+            p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+            m = m.to(DEV)
+            x = torch.rand(3, C, Hh, Ww)
+            x[:, 3] = (torch.rand(3, Hh, Ww) > 0.6).float() * torch.rand(3, Hh, Ww)
+            fu = torch.rand(3, 1, Hh, Ww)
+            chosen = random.sample(m.graph.offsets, 5)
+            cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=True, message_gain=0.3, hidden_only=True,
+                               zero_padded_shift=not torus)
+            ref = O.nca_step(x, p, cfg, 0.6, fu, chosen)
+            with torch.no_grad():
+                out = m.step(x.to(DEV), 0.6, fire_u=fu.to(DEV), chosen=chosen)
+            assert max_rel(out.cpu(), ref) < 1e-5, (C, torus, max_rel(out.cpu(), ref))
+
+
+def test_rejects_cpu_and_wrong_dtype():
+    m = graph_model(True)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 16, 40, 40), fire_rate=1.0)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 16, 40, 40, device=DEV, dtype=torch.float64), fire_rate=1.0)
