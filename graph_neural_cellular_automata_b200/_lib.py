@@ -37,6 +37,9 @@ EXPORTS = {
     # name: (restype, argtypes)
     "gnca_version": (C.c_int, []),
     "gnca_error_string": (C.c_char_p, [C.c_int]),
+    "gnca_launch_count": (C.c_ulonglong, []),
+    "gnca_profile_enable": (C.c_int, [C.c_int]),
+    "gnca_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "gnca_param_layout": (C.c_int, [C.POINTER(GncaModel), C.POINTER(GncaLayout)]),
     "gnca_pack_weights": (C.c_int, [C.POINTER(GncaModel), C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnca_perception_fwd": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 3),

@@ -677,7 +677,9 @@ static int launch_step_bwd(const gnca_model& m, const Packed& P, const float* pa
   const size_t smem = BwdSmem<C>::bytes(m.hidden, graph);
   if (smem > 226 * 1024) return GNCA_ERR_UNSUPPORTED;
   GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_mlp<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(PROF_BWD_MLP, st);
   k_bwd_mlp<C><<<A.nblocks, kBThreads, smem, st>>>(A, P, m.hidden, packed);
+  prof_end(PROF_BWD_MLP, st);
   GNCA_LAUNCH_CHECK();
   dim3 g3((a.H * a.W + 255) / 256, a.B);
   k_bwd_gather<C><<<g3, 256, 0, st>>>(A);

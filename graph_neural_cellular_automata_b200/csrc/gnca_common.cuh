@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <atomic>
 #include "../../include/gnca.h"
 
 #define GNCA_CHECK_CUDA(expr)                      \
@@ -12,13 +13,23 @@
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
+// every kernel launch in the library is followed by this macro: it also counts launches (gnca_launch_count)
 #define GNCA_LAUNCH_CHECK()                        \
   do {                                             \
+    ::gnca::g_launches.fetch_add(1, std::memory_order_relaxed); \
     cudaError_t _e = cudaGetLastError();           \
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
 namespace gnca {
+
+extern std::atomic<unsigned long long> g_launches;   // defined in gnca_fwd.cu
+
+// optional per-kernel timing with CUDA events on the launching stream (gnca_profile_enable / gnca_profile_read)
+enum ProfId { PROF_UPDATE = 0, PROF_APPLY = 1, PROF_RESIDENT_FWD = 2, PROF_BWD_MLP = 3, PROF_BWD_NORM = 4,
+              PROF_BWD_GATHER = 5, PROF_RESIDENT_BWD = 6, PROF_COUNT = 8 };
+void prof_begin(int id, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // Packed (kernel-side) weight buffer.  All offsets are multiples of 4 floats (float4 loads).

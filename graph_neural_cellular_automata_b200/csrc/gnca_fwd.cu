@@ -7,8 +7,27 @@
 // The cluster-resident multi-step kernel lives in gnca_resident.cu.
 #include "gnca_common.cuh"
 #include "gnca_internal.h"
+#include <vector>
+#include <utility>
 
 namespace gnca {
+
+std::atomic<unsigned long long> g_launches{0};
+
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev[PROF_COUNT];
+
+void prof_begin(int id, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, st);
+  g_prof_ev[id].push_back({a, b});
+}
+void prof_end(int id, cudaStream_t st) {
+  if (!g_prof_on || g_prof_ev[id].empty()) return;
+  cudaEventRecord(g_prof_ev[id].back().second, st);
+}
 
 constexpr int kChunk = 1024;    // cells per k_update block
 constexpr int kThreads = 256;
@@ -468,11 +487,15 @@ int launch_step_fwd(const gnca_model& m, const Packed& P, const float* packed, S
   const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
   GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 g1(a.nchunks, a.B);
+  prof_begin(PROF_UPDATE, st);
   k_update<C><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
+  prof_end(PROF_UPDATE, st);
   GNCA_LAUNCH_CHECK();
   const int tiles = ((a.W + kTileW - 1) / kTileW) * ((a.H + kTileH - 1) / kTileH);
   dim3 g2(tiles, a.B);
+  prof_begin(PROF_APPLY, st);
   k_apply<C><<<g2, kThreads, 0, st>>>(a, P, packed);
+  prof_end(PROF_APPLY, st);
   GNCA_LAUNCH_CHECK();
   if (attn_out) {
     if (!graph) return GNCA_ERR_ARG;
@@ -572,6 +595,29 @@ using namespace gnca;
 extern "C" {
 
 int gnca_version(void) { return GNCA_VERSION; }
+
+unsigned long long gnca_launch_count(void) { return g_launches.load(); }
+
+int gnca_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int gnca_profile_read(int kernel_id, double* total_ms, unsigned long long* launches) {
+  if (kernel_id < 0 || kernel_id >= PROF_COUNT || !total_ms || !launches) return GNCA_ERR_ARG;
+  double tot = 0.0;
+  unsigned long long n = 0;
+  for (auto& ev : g_prof_ev[kernel_id]) {
+    GNCA_CHECK_CUDA(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    GNCA_CHECK_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    tot += ms; ++n;
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  g_prof_ev[kernel_id].clear();
+  *total_ms = tot; *launches = n;
+  return 0;
+}
 
 const char* gnca_error_string(int code) {
   if (code == 0) return "ok";

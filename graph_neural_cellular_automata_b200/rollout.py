@@ -1,0 +1,193 @@
+"""Rollout = T CA steps in ONE library call (gnca_rollout_fwd / gnca_rollout_bwd).
+
+The reference has no rollout function: every script runs a Python `for` over `model(state[mask], fire_rate=fr)`
+(train_graph_augmented_nca.py:305-321, test_graph_augmented_regeneration.py:183-194, ...).  The contract of this
+extension is "equals T sequential `forward` calls given the same random draws".  A `Schedule` holds those draws
+on the device: per-step fire rate, message gain and offsets, per-sample step counts, and the fire uniforms
+(either a recorded/pre-drawn tensor or an in-kernel Philox stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import functional as GF
+from ._lib import GncaSchedule
+
+Offset = Tuple[int, int]
+
+
+@dataclass
+class Schedule:
+    """Device-resident per-step schedule of a rollout (mirror of `gnca_schedule` in include/gnca.h)."""
+    T: int
+    k: int
+    fire_rate: torch.Tensor                 # [T] f32
+    message_gain: torch.Tensor              # [T] f32
+    offsets: Optional[torch.Tensor]         # [T,k,2] int8
+    steps: Optional[torch.Tensor] = None    # [B] int32
+    fire_u: Optional[torch.Tensor] = None   # [T,B,H,W] f32 (row b = sample b)
+    philox_seed: int = 0
+    philox_offset: int = 0
+    damage: Optional[torch.Tensor] = None   # [B,C,H,W] multiplicative mask
+    damage_step: int = 0
+    total_updates: Optional[int] = None     # sum_b steps_b (host int, for throughput accounting)
+
+    def c_struct(self) -> GncaSchedule:
+        p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        return GncaSchedule(self.T, self.k, p(self.fire_rate), p(self.message_gain), p(self.offsets), p(self.steps),
+                            p(self.fire_u), C.c_uint64(self.philox_seed), C.c_uint64(self.philox_offset),
+                            p(self.damage), self.damage_step)
+
+
+def _upload(arrs: Sequence[np.ndarray], device) -> List[torch.Tensor]:
+    """One pinned staging buffer, one async H2D copy, typed device views."""
+    sizes = [a.nbytes for a in arrs]
+    offs, o = [], 0
+    for s in sizes:
+        offs.append(o)
+        o += (s + 15) // 16 * 16
+    host = torch.empty(max(o, 16), dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else torch.empty(max(o, 16), dtype=torch.uint8)
+    hv = host.numpy()
+    for a, off in zip(arrs, offs):
+        hv[off:off + a.nbytes] = np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8)
+    dev = host.to(device, non_blocking=True)
+    out = []
+    for a, off in zip(arrs, offs):
+        t = dev[off:off + a.nbytes].view(torch.from_numpy(np.empty(0, a.dtype)).dtype).view(a.shape)
+        out.append(t)
+    return out
+
+
+def make_schedule(model, B: int, H: int, W: int, T: int, *, fire_rate: Union[float, Sequence[float]] = 1.0,
+                  message_gains: Optional[Sequence[float]] = None, message_every: int = 1,
+                  offsets: Optional[Sequence[Sequence[Offset]]] = None, steps: Optional[Sequence[int]] = None,
+                  fire: str = "philox", fire_u: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+                  damage: Optional[torch.Tensor] = None, damage_step: int = 0, device=None) -> Schedule:
+    """Build the schedule the way T sequential `forward` calls would consume randomness.
+
+    * offsets: drawn with `random.sample(model.graph.offsets, k)` once per step (graph models), exactly like
+      graph_augmentation.py:120-121, unless given.
+    * fire="torch": one `torch.rand(B,1,H,W)` per step on the model device (bit-identical stream to T forward
+      calls with a fixed fire_rate < 1); fire="philox": in-kernel Philox4x32-10 keyed by `seed` (no HBM traffic,
+      statistically equivalent, different numbers); or pass recorded `fire_u` [T,B,H,W].
+    * message_gains: per-step `model.message_gain` (the trainer sets gain or 0 per step, train...:312-319);
+      default = model.message_gain on steps with t % message_every == 0, else 0.
+    """
+    device = device or next(model.parameters()).device
+    is_graph = bool(getattr(model, "_is_graph", False))
+    fr = np.full(T, float(fire_rate), np.float32) if np.isscalar(fire_rate) else np.asarray(fire_rate, np.float32)
+    assert fr.shape == (T,)
+    if is_graph:
+        if offsets is None:
+            offsets = [model.graph.draw_offsets() for _ in range(T)]
+        k = len(offsets[0]) if T > 0 else 0
+        off = np.asarray(offsets, dtype=np.int8).reshape(T, k, 2) if k > 0 else np.zeros((T, 0, 2), np.int8)
+        if message_gains is None:
+            g = float(model.message_gain)
+            message_gains = [g if (message_every <= 1 or t % message_every == 0) else 0.0 for t in range(T)]
+    else:
+        k, off = 0, np.zeros((T, 0, 2), np.int8)
+        message_gains = [0.0] * T
+    gains = np.asarray(message_gains, np.float32)
+    arrs = [fr, gains, off if off.size else np.zeros(2, np.int8)]
+    if steps is not None:
+        st = np.asarray(steps, np.int32)
+        assert st.shape == (B,)
+        arrs.append(st)
+        total = int(np.minimum(st, T).clip(min=0).sum())
+    else:
+        total = B * T
+    dev = _upload(arrs, device)
+    sched = Schedule(T=T, k=k, fire_rate=dev[0], message_gain=dev[1], offsets=dev[2] if off.size else None,
+                     steps=dev[3] if steps is not None else None, damage=damage, damage_step=int(damage_step),
+                     total_updates=total)
+    needs_fire = bool((fr < 1.0).any())
+    if fire_u is not None:
+        sched.fire_u = GF._require_cuda_f32(fire_u, "fire_u").view(T, B, H, W)
+    elif needs_fire and fire == "torch":
+        buf = torch.empty(T, B, 1, H, W, dtype=torch.float32, device=device)
+        for t in range(T):
+            if fr[t] < 1.0:
+                torch.rand(B, 1, H, W, out=buf[t])
+        sched.fire_u = buf.view(T, B, H, W)
+    elif needs_fire:
+        if fire != "philox":
+            raise ValueError("fire must be 'torch' or 'philox'")
+        sched.philox_seed = int(seed if seed is not None else random.getrandbits(63))
+    return sched
+
+
+class _RolloutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, cfg, *params):
+        desc = cfg["desc"]
+        sched: Schedule = cfg["schedule"]
+        x0 = GF._require_cuda_f32(x0, "x0")
+        B, Cc, H, W = x0.shape
+        if Cc != desc.C:
+            raise RuntimeError(f"x0 has {Cc} channels, model has {desc.C}")
+        lib = _lib.load()
+        need_grad = cfg["need_grad"]
+        T = sched.T
+        xT = torch.empty_like(x0)
+        hist = torch.empty(T + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device) if (need_grad or cfg["history"]) else None
+        nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, T)
+        ws = GF._WS.get(x0.device, nbytes)
+        cs = sched.c_struct()
+        _lib.check(lib.gnca_rollout_fwd(C.byref(desc), GF._ptr(cfg["packed"]), B, H, W, C.byref(cs), GF._ptr(x0),
+                                        GF._ptr(xT), GF._ptr(hist), C.c_void_p(0), GF._ptr(ws), ws.numel(),
+                                        int(cfg["impl"]), GF._stream()), "gnca_rollout_fwd")
+        ctx.cfg = cfg
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.hist = hist
+        if cfg["history"]:
+            ctx.mark_non_differentiable(hist)
+            return xT, hist
+        return xT
+
+    @staticmethod
+    def backward(ctx, gT, *unused):
+        cfg = ctx.cfg
+        desc = cfg["desc"]
+        sched: Schedule = cfg["schedule"]
+        hist = ctx.hist
+        if hist is None:
+            raise RuntimeError("rollout was run without gradient history")
+        _, B, Cc, H, W = hist.shape
+        gT = GF._require_cuda_f32(gT, "grad_output")
+        lib = _lib.load()
+        lay = GF.param_layout(desc)
+        g0 = torch.empty_like(gT)
+        gflat = torch.zeros(lay.total, dtype=torch.float32, device=gT.device)
+        nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, sched.T)
+        ws = GF._WS.get(gT.device, nbytes)
+        cs = sched.c_struct()
+        _lib.check(lib.gnca_rollout_bwd(C.byref(desc), GF._ptr(cfg["packed"]), B, H, W, C.byref(cs), GF._ptr(hist),
+                                        C.c_void_p(0), GF._ptr(gT), GF._ptr(g0), GF._ptr(gflat), GF._ptr(ws),
+                                        ws.numel(), int(cfg["impl"]), GF._stream()), "gnca_rollout_bwd")
+        offs = GF.segment_offsets(desc)
+        grads = [gflat[offs[i]:offs[i + 1]].view(ctx.param_shapes[i]) for i in range(len(ctx.param_shapes))]
+        ctx.hist = None
+        return (g0, None, *grads)
+
+
+IMPL = {"auto": 0, "streaming": 1, "resident": 2}
+
+
+def rollout(model, x0: torch.Tensor, schedule: Schedule, *, return_history: bool = False, impl: str = "auto"):
+    """x_T (and optionally the [T+1,B,C,H,W] history) of T steps from x0 under `schedule`.  Differentiable
+    w.r.t. x0 and the model parameters (BPTT stores x_t only and recomputes the rest)."""
+    if not x0.is_cuda:
+        raise RuntimeError(f"rollout: x0 is on {x0.device}; CUDA (sm_100a) only, no CPU fallback")
+    ps = model.canonical_params()
+    need_grad = torch.is_grad_enabled() and (x0.requires_grad or any(p.requires_grad for p in ps))
+    cfg = {"desc": model.model_desc(), "packed": model.packed_weights(), "schedule": schedule, "need_grad": need_grad,
+           "history": bool(return_history), "impl": IMPL[impl]}
+    return _RolloutFn.apply(x0, cfg, *ps)

@@ -90,6 +90,13 @@ typedef struct gnca_schedule {
 
 int gnca_version(void);
 const char* gnca_error_string(int code);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+unsigned long long gnca_launch_count(void);
+/* Optional per-kernel timing (CUDA events on the launching stream around each launch of the kernel family):
+ * ids 0 k_update, 1 k_apply, 2 resident forward rollout, 3 k_bwd_mlp, 6 resident backward.  read() waits for the
+ * recorded events, returns the summed duration and launch count since the last read, and clears them. */
+int gnca_profile_enable(int on);
+int gnca_profile_read(int kernel_id, double* total_ms, unsigned long long* launches);
 
 int gnca_param_layout(const gnca_model* m, gnca_layout* out);
 /* canonical flat params -> packed kernel-side buffer (packed_total floats) */

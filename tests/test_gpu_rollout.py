@@ -1,0 +1,145 @@
+"""GPU parity of the rollout entry points (gnca_rollout_fwd/_bwd through rollout.py) against golden fixtures."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, load_params, max_rel, rel_err
+from oracle import nca_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import graph_neural_cellular_automata_b200 as G
+    from graph_neural_cellular_automata_b200 import functional as GF
+    from graph_neural_cellular_automata_b200.rollout import make_schedule, rollout
+    from test_gpu_step import graph_model, classic_model, T32, tup, DEV
+
+IMPLS = ["streaming", "resident"]
+
+
+def _supported(impl, fn):
+    from graph_neural_cellular_automata_b200._lib import GncaError
+    try:
+        return fn()
+    except GncaError as e:
+        if impl == "resident" and "unsupported" in str(e):
+            pytest.skip("resident kernel not available for this configuration")
+        raise
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_rollout_matches_golden_torus(impl):
+    g = load_golden("graph_torus_rollout.npz")
+    m = graph_model(True)
+    x0 = T32(g["x_0"]).to(DEV)
+    T = 48
+    sched = make_schedule(m, 2, 40, 40, T, fire_rate=float(g["fire_rate"]), offsets=[tup(c) for c in g["chosen"]],
+                          fire_u=T32(g["fire_u"]).to(DEV))
+    with torch.no_grad():
+        xT, hist = _supported(impl, lambda: rollout(m, x0, sched, return_history=True, impl=impl))
+    assert torch.equal(hist[T], xT)
+    for t in (1, 8, 16, 32, 48):
+        ref = T32(g[f"x_{t}"])
+        assert rel_err(hist[t].cpu(), ref) < 1e-5, (t, rel_err(hist[t].cpu(), ref))
+        assert torch.equal(GF.alive_mask(hist[t], 0.12).cpu(), O.alive_mask(ref, 0.12)), t
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_rollout_equals_sequential_steps(impl):
+    """The contract of the extension: bit-identical to T module.step() calls with the same draws."""
+    m = graph_model(True)
+    g = load_golden("graph_torus_step.npz")
+    x0 = T32(g["x_in"]).to(DEV)
+    T = 7
+    random.seed(3)
+    offs = [m.graph.draw_offsets() for _ in range(T)]
+    fu = torch.rand(T, 2, 40, 40, device=DEV)
+    gains = [0.25 if t % 3 == 0 else 0.0 for t in range(T)]
+    frs = [0.5 + 0.05 * t for t in range(T)]
+    sched = make_schedule(m, 2, 40, 40, T, fire_rate=frs, offsets=offs, fire_u=fu, message_gains=gains)
+    with torch.no_grad():
+        xT = _supported(impl, lambda: rollout(m, x0, sched, impl=impl))
+        x = x0
+        for t in range(T):
+            x = m.step(x, frs[t], fire_u=fu[t].unsqueeze(1), chosen=offs[t], message_gain=gains[t])
+    if impl == "streaming":
+        assert torch.equal(xT, x)
+    else:
+        assert rel_err(xT.cpu(), x.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("fname,kind", [("graph_torus_grads.npz", "graph"), ("graph_torus_grads_ragged.npz", "graph"),
+                                        ("classic_grads.npz", "classic")])
+def test_rollout_grads_golden(impl, fname, kind):
+    g = load_golden(fname)
+    m = graph_model(True) if kind == "graph" else classic_model()
+    T = len(g["gains"])
+    B = g["x0"].shape[0]
+    x0 = T32(g["x0"]).to(DEV).requires_grad_(True)
+    steps = g["steps"].tolist() if "steps" in g else None
+    sched = make_schedule(m, B, 40, 40, T, fire_rate=g["fire_rates"].tolist(),
+                          offsets=[tup(c) for c in g["chosen"]] if kind == "graph" else None,
+                          fire_u=T32(g["fire_u"]).to(DEV), message_gains=g["gains"].tolist(), steps=steps)
+    target = T32(np.load(os.path.join(GOLDEN, "target_gecko_surrogate.npy"))).to(DEV)
+    xT = _supported(impl, lambda: rollout(m, x0, sched, impl=impl))
+    pred = xT[:, :4]
+    rgba = torch.cat([pred[:, :3] * pred[:, 3:4], pred[:, 3:4]], 1)
+    per = ((rgba - target.unsqueeze(0)) ** 2).mean(dim=(1, 2, 3))
+    per.mean().backward()
+    assert rel_err(xT.detach().cpu(), g["x_T"]) < 1e-5
+    assert rel_err(per.detach().cpu(), g["per_sample"]) < 1e-5       # 1e-5 rel loss
+    assert rel_err(x0.grad.cpu(), g["grad_x0"]) < 1e-4
+    named = dict(m.named_parameters())
+    for k, v in g.items():
+        if not k.startswith("grad:") or v.size == 0:
+            continue
+        name = k[5:]
+        ours = named[name].grad if named[name].grad is not None else torch.zeros_like(named[name])
+        if kind == "graph" and any(s in name for s in ("query_proj", "key_proj", "scaling")):
+            assert float(ours.abs().max()) <= 1e-8, name
+        else:
+            assert rel_err(ours.cpu(), v) < 1e-4, (name, rel_err(ours.cpu(), v))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_philox_fire_stream(impl):
+    """In-kernel Philox fire masks: deterministic per seed, fire fraction ~ fire_rate, differs across seeds."""
+    m = graph_model(True)
+    x0 = T32(load_golden("graph_torus_step.npz")["x_in"]).to(DEV)
+    random.seed(1)
+    s1 = make_schedule(m, 2, 40, 40, 5, fire_rate=0.5, seed=11)
+    random.seed(1)
+    s2 = make_schedule(m, 2, 40, 40, 5, fire_rate=0.5, seed=11)
+    random.seed(1)
+    s3 = make_schedule(m, 2, 40, 40, 5, fire_rate=0.5, seed=12)
+    with torch.no_grad():
+        a = _supported(impl, lambda: rollout(m, x0, s1, impl=impl))
+        b = rollout(m, x0, s2, impl=impl)
+        c = rollout(m, x0, s3, impl=impl)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert torch.isfinite(a).all()
+
+
+def test_damage_in_rollout():
+    """A multiplicative damage mask at step t (regeneration test, test_graph_augmented_regeneration.py:185-189)."""
+    m = graph_model(True)
+    g = load_golden("graph_torus_step.npz")
+    x0 = T32(g["x_in"]).to(DEV)
+    T, td = 6, 3
+    D = O.damage_mask("circle", 2, 16, 40, 40, size=6, pos=[(20, 20), (18, 22)]).to(DEV)
+    random.seed(9)
+    offs = [m.graph.draw_offsets() for _ in range(T)]
+    fu = torch.rand(T, 2, 40, 40, device=DEV)
+    sched = make_schedule(m, 2, 40, 40, T, fire_rate=0.5, offsets=offs, fire_u=fu, damage=D, damage_step=td)
+    with torch.no_grad():
+        xT = rollout(m, x0, sched, impl="streaming")
+        x = x0
+        for t in range(T):
+            if t == td:
+                x = x * D
+            x = m.step(x, 0.5, fire_u=fu[t].unsqueeze(1), chosen=offs[t])
+    assert torch.equal(xT, x)
