@@ -30,4 +30,10 @@ int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, cons
                  const float* gout, float* gx, float* gparams, void* bwd_ws, bool zero_partials, bool reduce_partials,
                  cudaStream_t st);
 
+// cluster-resident forward rollout (gnca_resident.cu); GNCA_ERR_UNSUPPORTED when the configuration has no
+// resident kernel (zero-padded graph shift, sample too large for the cluster's shared memory)
+int run_resident_fwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,
+                     const gnca_schedule& sched, const float* x0, float* xT, float* hist, float* stats_hist,
+                     float* ping, float* pong, float* alpha_tmp, cudaStream_t st);
+
 }  // namespace gnca

@@ -19,6 +19,7 @@ struct RolloutWorkspace {
   float* stats;    // [B][2]
   float* g_a;      // gradient ping-pong
   float* g_b;
+  float* alpha_tmp;  // [B][H][W] (resident kernel)
   char* step_ws;   // forward + backward per-step workspace
   size_t step_bytes;
   size_t bytes;
@@ -37,6 +38,7 @@ static RolloutWorkspace carve_rollout(void* base, const gnca_model& m, int B, in
   r.g_a = reinterpret_cast<float*>(p + o); o = al(o + N);
   r.g_b = reinterpret_cast<float*>(p + o); o = al(o + N);
   r.stats = reinterpret_cast<float*>(p + o); o = al(o + (size_t)B * 2 * sizeof(float));
+  r.alpha_tmp = reinterpret_cast<float*>(p + o); o = al(o + (size_t)B * H * W * sizeof(float));
   r.step_ws = p + o;
   r.step_bytes = carve_fwd_workspace(nullptr, m, B, H, W).bytes + bwd_workspace_bytes(m, B, H, W);
   o = al(o + r.step_bytes);
@@ -78,7 +80,6 @@ int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H,
   if (sched->T > 0 && (!sched->fire_rate || (graph && !sched->message_gain))) return GNCA_ERR_ARG;
   if (graph && sched->k > 0 && !sched->offsets) return GNCA_ERR_ARG;
   if (sched->k < 0 || sched->k > GNCA_MAX_K) return GNCA_ERR_UNSUPPORTED;
-  if (impl == 2) return GNCA_ERR_UNSUPPORTED;   // TODO(resident)
   cudaStream_t st = (cudaStream_t)stream;
   RolloutWorkspace r = carve_rollout(workspace_dev, *m, B, H, W);
   if (r.bytes > workspace_bytes) return GNCA_ERR_WORKSPACE;
@@ -86,6 +87,15 @@ int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H,
   const Packed P = make_packed(m->C, m->hidden, m->d_model, graph);
   FwdWorkspace fws = carve_fwd_workspace(r.step_ws, *m, B, H, W);
   const int T = sched->T;
+  if (impl != 1 && T > 0) {
+    // auto: small samples (the launch-latency-bound regime) go to the cluster-resident kernel
+    const bool want = impl == 2 || (size_t)H * W <= 16384;
+    if (want) {
+      int rc = run_resident_fwd(*m, P, packed_dev, B, H, W, *sched, x0_dev, xT_dev, x_hist_dev, stats_hist_dev, r.ping,
+                                r.pong, r.alpha_tmp, st);
+      if (rc != GNCA_ERR_UNSUPPORTED || impl == 2) return rc;
+    }
+  }
 
   // where x_t lives: x_hist slices when a history is requested, else ping/pong (x_T straight into xT_dev)
   auto x_at = [&](int t) -> float* {
