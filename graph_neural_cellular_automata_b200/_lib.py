@@ -30,7 +30,7 @@ class GncaSchedule(C.Structure):
     _fields_ = [("T", C.c_int32), ("k", C.c_int32), ("fire_rate", C.c_void_p), ("message_gain", C.c_void_p),
                 ("offsets", C.c_void_p), ("steps", C.c_void_p), ("fire_u", C.c_void_p),
                 ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("damage", C.c_void_p),
-                ("damage_step", C.c_int32)]
+                ("damage_step", C.c_int32), ("max_offset", C.c_int32)]
 
 
 EXPORTS = {

@@ -132,7 +132,7 @@ int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H,
     return GNCA_ERR_ARG;
   if (B <= 0 || H <= 0 || W <= 0 || sched->T < 0) return GNCA_ERR_ARG;
   if (!model_supported(*m)) return GNCA_ERR_UNSUPPORTED;
-  if (impl == 2) return GNCA_ERR_UNSUPPORTED;   // TODO(resident)
+  (void)impl;             // the backward currently always takes the streaming kernels (x_hist layout is shared)
   (void)stats_hist_dev;   // statistics are recomputed together with u
   const bool graph = (m->flags & GNCA_F_GRAPH) != 0;
   cudaStream_t st = (cudaStream_t)stream;

@@ -38,12 +38,13 @@ class Schedule:
     damage: Optional[torch.Tensor] = None   # [B,C,H,W] multiplicative mask
     damage_step: int = 0
     total_updates: Optional[int] = None     # sum_b steps_b (host int, for throughput accounting)
+    max_offset: int = 0                     # max(|dy|,|dx|) over the offsets (halo depth of the resident kernel)
 
     def c_struct(self) -> GncaSchedule:
         p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
         return GncaSchedule(self.T, self.k, p(self.fire_rate), p(self.message_gain), p(self.offsets), p(self.steps),
                             p(self.fire_u), C.c_uint64(self.philox_seed), C.c_uint64(self.philox_offset),
-                            p(self.damage), self.damage_step)
+                            p(self.damage), self.damage_step, self.max_offset)
 
 
 def _upload(arrs: Sequence[np.ndarray], device) -> List[torch.Tensor]:
@@ -107,7 +108,7 @@ def make_schedule(model, B: int, H: int, W: int, T: int, *, fire_rate: Union[flo
     dev = _upload(arrs, device)
     sched = Schedule(T=T, k=k, fire_rate=dev[0], message_gain=dev[1], offsets=dev[2] if off.size else None,
                      steps=dev[3] if steps is not None else None, damage=damage, damage_step=int(damage_step),
-                     total_updates=total)
+                     total_updates=total, max_offset=int(np.abs(off).max()) if off.size else 0)
     needs_fire = bool((fr < 1.0).any())
     if fire_u is not None:
         sched.fire_u = GF._require_cuda_f32(fire_u, "fire_u").view(T, B, H, W)

@@ -86,6 +86,7 @@ typedef struct gnca_schedule {
   uint64_t philox_offset;
   const float* damage;        /* [B][C][H][W] multiplicative mask applied to x BEFORE step damage_step, or NULL */
   int32_t damage_step;
+  int32_t max_offset;         /* max(|dy|,|dx|) over all offsets (halo depth of the resident kernel); 0 = unknown */
 } gnca_schedule;
 
 int gnca_version(void);
