@@ -74,6 +74,11 @@ class FusedStepMixin:
             fire_u = torch.rand(x.shape[0], 1, x.shape[2], x.shape[3], device=x.device)
         return self._fused_step(x, fire_rate, fire_u, chosen=chosen, message_gain=gain, want_attn=return_attention)
 
+    def invalidate_packed(self) -> None:
+        """Drop the cached kernel-side weights (needed after an optimiser writes the parameters through raw
+        device pointers, which does not bump the tensors' version counters)."""
+        self.__dict__.pop("_gnca_packed", None)
+
     def _fused_step(self, x, fire_rate, fire_u, *, chosen: Sequence[Tuple[int, int]], message_gain: float,
                     want_attn: bool = False):
         if not x.is_cuda:

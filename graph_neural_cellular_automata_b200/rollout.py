@@ -125,26 +125,49 @@ def make_schedule(model, B: int, H: int, W: int, T: int, *, fire_rate: Union[flo
     return sched
 
 
+def rollout_fwd_raw(desc, packed, x0: torch.Tensor, sched: Schedule, *, history: bool, impl: int = 0):
+    """gnca_rollout_fwd without autograd: returns (x_T, x_hist or None)."""
+    x0 = GF._require_cuda_f32(x0, "x0")
+    B, Cc, H, W = x0.shape
+    if Cc != desc.C:
+        raise RuntimeError(f"x0 has {Cc} channels, model has {desc.C}")
+    lib = _lib.load()
+    T = sched.T
+    xT = torch.empty_like(x0)
+    hist = torch.empty(T + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device) if history else None
+    nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, T)
+    ws = GF._WS.get(x0.device, nbytes)
+    cs = sched.c_struct()
+    _lib.check(lib.gnca_rollout_fwd(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(x0), GF._ptr(xT),
+                                    GF._ptr(hist), C.c_void_p(0), GF._ptr(ws), ws.numel(), int(impl), GF._stream()),
+               "gnca_rollout_fwd")
+    return xT, hist
+
+
+def rollout_bwd_raw(desc, packed, hist: torch.Tensor, sched: Schedule, gT: torch.Tensor, *, gflat=None, impl: int = 0):
+    """gnca_rollout_bwd without autograd: returns (dL/dx_0, flat parameter gradient in canonical layout).
+    `gflat` (optional) is accumulated into."""
+    _, B, Cc, H, W = hist.shape
+    gT = GF._require_cuda_f32(gT, "grad_output")
+    lib = _lib.load()
+    lay = GF.param_layout(desc)
+    g0 = torch.empty_like(gT)
+    if gflat is None:
+        gflat = torch.zeros(lay.total, dtype=torch.float32, device=gT.device)
+    nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, sched.T)
+    ws = GF._WS.get(gT.device, nbytes)
+    cs = sched.c_struct()
+    _lib.check(lib.gnca_rollout_bwd(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(hist), C.c_void_p(0),
+                                    GF._ptr(gT), GF._ptr(g0), GF._ptr(gflat), GF._ptr(ws), ws.numel(), int(impl),
+                                    GF._stream()), "gnca_rollout_bwd")
+    return g0, gflat
+
+
 class _RolloutFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x0, cfg, *params):
-        desc = cfg["desc"]
-        sched: Schedule = cfg["schedule"]
-        x0 = GF._require_cuda_f32(x0, "x0")
-        B, Cc, H, W = x0.shape
-        if Cc != desc.C:
-            raise RuntimeError(f"x0 has {Cc} channels, model has {desc.C}")
-        lib = _lib.load()
-        need_grad = cfg["need_grad"]
-        T = sched.T
-        xT = torch.empty_like(x0)
-        hist = torch.empty(T + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device) if (need_grad or cfg["history"]) else None
-        nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, T)
-        ws = GF._WS.get(x0.device, nbytes)
-        cs = sched.c_struct()
-        _lib.check(lib.gnca_rollout_fwd(C.byref(desc), GF._ptr(cfg["packed"]), B, H, W, C.byref(cs), GF._ptr(x0),
-                                        GF._ptr(xT), GF._ptr(hist), C.c_void_p(0), GF._ptr(ws), ws.numel(),
-                                        int(cfg["impl"]), GF._stream()), "gnca_rollout_fwd")
+        xT, hist = rollout_fwd_raw(cfg["desc"], cfg["packed"], x0, cfg["schedule"],
+                                   history=bool(cfg["need_grad"] or cfg["history"]), impl=cfg["impl"])
         ctx.cfg = cfg
         ctx.param_shapes = [p.shape for p in params]
         ctx.hist = hist
@@ -156,24 +179,10 @@ class _RolloutFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gT, *unused):
         cfg = ctx.cfg
-        desc = cfg["desc"]
-        sched: Schedule = cfg["schedule"]
-        hist = ctx.hist
-        if hist is None:
+        if ctx.hist is None:
             raise RuntimeError("rollout was run without gradient history")
-        _, B, Cc, H, W = hist.shape
-        gT = GF._require_cuda_f32(gT, "grad_output")
-        lib = _lib.load()
-        lay = GF.param_layout(desc)
-        g0 = torch.empty_like(gT)
-        gflat = torch.zeros(lay.total, dtype=torch.float32, device=gT.device)
-        nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, sched.T)
-        ws = GF._WS.get(gT.device, nbytes)
-        cs = sched.c_struct()
-        _lib.check(lib.gnca_rollout_bwd(C.byref(desc), GF._ptr(cfg["packed"]), B, H, W, C.byref(cs), GF._ptr(hist),
-                                        C.c_void_p(0), GF._ptr(gT), GF._ptr(g0), GF._ptr(gflat), GF._ptr(ws),
-                                        ws.numel(), int(cfg["impl"]), GF._stream()), "gnca_rollout_bwd")
-        offs = GF.segment_offsets(desc)
+        g0, gflat = rollout_bwd_raw(cfg["desc"], cfg["packed"], ctx.hist, cfg["schedule"], gT, impl=cfg["impl"])
+        offs = GF.segment_offsets(cfg["desc"])
         grads = [gflat[offs[i]:offs[i + 1]].view(ctx.param_shapes[i]) for i in range(len(ctx.param_shapes))]
         ctx.hist = None
         return (g0, None, *grads)
