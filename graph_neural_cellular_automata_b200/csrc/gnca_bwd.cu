@@ -50,6 +50,10 @@ struct BwdArgs {
   int ntiles, nblocks, n_items, nchunks;
   int64_t wtotal;
   gnca_layout L;
+  const float* zp_rowsum;   // row sums of x (zero-padded shift)
+  AttnBwdScratch zp_scratch;
+  float* gw_part;           // [B][nchunks][GNCA_MAX_K] dL/dw_i partials (zero-padded shift) or null
+  const float* grow;        // [B][C][H] additive row term of dL/dx from the attention weights, or null
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -191,7 +195,7 @@ struct BwdSmem {
     f += C;                                                                                // gamma
     if (graph) f += C * C + C;                                                             // Wm, bm
     f += (size_t)(3 * C + C + 2 * hid) * K::NBP;                                           // Yt, GDt, Ht, GHt
-    if (graph) f += (size_t)(2 * C + 1) * K::NBP;                                          // XSt, GAt, AS
+    if (graph) f += (size_t)(3 * C + 2) * K::NBP;                                          // XSt, GAt, GXSt, AS, GB
     return f;
   }
   static size_t bytes(int hid, bool graph) {
@@ -231,8 +235,10 @@ __global__ void __launch_bounds__(kBThreads) k_bwd_mlp(BwdArgs A, Packed P, int 
   float* GHt = Ht + hid * NBP;
   float* XSt = GHt + hid * NBP;
   float* GAt = XSt + (graph ? C * NBP : 0);
-  float* AS = GAt + (graph ? C * NBP : 0);
-  float* endf = AS + (graph ? NBP : 0);
+  float* GXSt = GAt + (graph ? C * NBP : 0);
+  float* AS = GXSt + (graph ? C * NBP : 0);
+  float* GB = AS + (graph ? NBP : 0);
+  float* endf = GB + (graph ? NBP : 0);
   uint16_t* slist = reinterpret_cast<uint16_t*>(endf);
   int* scell = reinterpret_cast<int*>(slist + kBChunk);
   __shared__ int s_nact;
@@ -527,11 +533,36 @@ __global__ void __launch_bounds__(kBThreads) k_bwd_mlp(BwdArgs A, Packed P, int 
         }
         for (int idx = threadIdx.x; idx < NB * C; idx += kBThreads) {
           const int cl = idx % NB, ci = idx / NB;
-          if (cl >= nb) continue;
           float v = 0.f;
+          if (cl < nb) {
 #pragma unroll 4
-          for (int co = 0; co < C; ++co) v = fmaf(sWm[co * C + ci], GAt[co * NBP + cl], v);
-          A.gxs[((size_t)b * C + ci) * HW + scell[cl]] = v;
+            for (int co = 0; co < C; ++co) v = fmaf(sWm[co * C + ci], GAt[co * NBP + cl], v);
+            A.gxs[((size_t)b * C + ci) * HW + scell[cl]] = v;
+          }
+          GXSt[ci * NBP + cl] = v;
+        }
+        if (A.gw_part) {   // zero-padded shift: dL/dw_i += sum_p [ g_xs(p) . A x(q_i(p)) + (bm . g_agg(p)) A(q_i(p)) ]
+          for (int cl = threadIdx.x; cl < NB; cl += kBThreads) {
+            float gb = 0.f;
+            for (int c = 0; c < C; ++c) gb = fmaf(sbm[c], GAt[c * NBP + cl], gb);
+            GB[cl] = gb;
+          }
+          __syncthreads();
+          for (int oi = threadIdx.x; oi < a.k; oi += kBThreads) {
+            int dy, dx;
+            step_offset(a, oi, dy, dx);
+            float acc = 0.f;
+            for (int cl = 0; cl < nb; ++cl) {
+              const int pc = scell[cl], py = pc / W, px = pc - py * W;
+              int qy, qx;
+              if (!sender_of(py, px, dy, dx, H, W, torus, qy, qx)) continue;
+              if (a2a && !alive_at(xs_base + 3 * HW, qy, qx, H, W, a.graph_alpha_thr)) continue;
+              float v = GB[cl];
+              for (int c = 0; c < C; ++c) v = fmaf(GXSt[c * NBP + cl], __ldg(xs_base + (size_t)c * HW + qy * W + qx), v);
+              acc += v;
+            }
+            A.gw_part[((size_t)b * A.nchunks + chunk) * GNCA_MAX_K + oi] += acc;
+          }
         }
       }
       __syncthreads();
@@ -611,6 +642,10 @@ __global__ void __launch_bounds__(256) k_bwd_gather(BwdArgs A) {
       }
     }
   }
+  if (A.grow) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) g[c] += A.grow[((size_t)b * C + c) * H + y];
+  }
 #pragma unroll
   for (int c = 0; c < C; ++c) gxp[(size_t)c * HW] = g[c];
 }
@@ -634,6 +669,8 @@ struct BwdWorkspace {
   double* tile_part;
   size_t bytes;
   size_t wpart_bytes;
+  AttnBwdScratch attn;
+  size_t gw_bytes;
 };
 
 static BwdWorkspace carve_bwd(void* base, const gnca_model& m, int B, int H, int W) {
@@ -653,6 +690,10 @@ static BwdWorkspace carve_bwd(void* base, const gnca_model& m, int B, int H, int
   w.wpart = reinterpret_cast<float*>(p + o);
   w.wpart_bytes = (size_t)kMaxBwdBlocks * L.total * 4;
   o = align_up_b(o + w.wpart_bytes, 256);
+  const int nchunks = (H * W + kBChunk - 1) / kBChunk;
+  w.attn = carve_attn_bwd(p + o, m, B, H, nchunks);
+  w.gw_bytes = (size_t)B * nchunks * GNCA_MAX_K * 4;
+  o += ((m.flags & GNCA_F_GRAPH) ? attn_bwd_scratch_bytes(m, B, H, nchunks) : 0);
   w.bytes = o;
   return w;
 }
@@ -664,9 +705,6 @@ static int launch_step_bwd(const gnca_model& m, const Packed& P, const float* pa
                            cudaStream_t st) {
   const StepArgs& a = A.s;
   const bool graph = (m.flags & GNCA_F_GRAPH) != 0;
-  // zero-padded shift: the softmax weights depend on x and on Wq/Wk/scaling; that gradient path is not built yet
-  if (graph && !(m.flags & GNCA_F_TORUS) && a.k > 0 && (a.message_gain_dev || a.message_gain != 0.f))
-    return GNCA_ERR_UNSUPPORTED;
   dim3 g1(A.ntiles, a.B);
   k_bwd_norm<C><<<g1, kBThreads, 0, st>>>(A, P, packed);
   GNCA_LAUNCH_CHECK();
@@ -681,6 +719,10 @@ static int launch_step_bwd(const gnca_model& m, const Packed& P, const float* pa
   k_bwd_mlp<C><<<A.nblocks, kBThreads, smem, st>>>(A, P, m.hidden, packed);
   prof_end(PROF_BWD_MLP, st);
   GNCA_LAUNCH_CHECK();
+  if (A.gw_part) {
+    int rc = run_attn_bwd(m, P, packed, a, A.zp_rowsum, A.zp_scratch, A.nchunks, gparams, st);
+    if (rc) return rc;
+  }
   dim3 g3((a.H * a.W + 255) / 256, a.B);
   k_bwd_gather<C><<<g3, 256, 0, st>>>(A);
   GNCA_LAUNCH_CHECK();
@@ -699,12 +741,25 @@ int dispatch_step_bwd(const gnca_model& m, const Packed& P, const float* packed,
 }
 
 
-int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, const StepArgs& a, const float* stats,
-                 const float* gout, float* gx, float* gparams, void* bwd_ws, bool zero_partials, bool reduce_partials,
-                 cudaStream_t st) {
-  BwdWorkspace w = carve_bwd(bwd_ws, m, a.B, a.H, a.W);
+int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, const StepArgs& a_in, const float* stats,
+                 const float* gout, float* gx, float* gparams, const FwdWorkspace& fws, void* bwd_ws, bool zero_partials,
+                 bool reduce_partials, cudaStream_t st) {
+  BwdWorkspace w = carve_bwd(bwd_ws, m, a_in.B, a_in.H, a_in.W);
+  StepArgs a = a_in;
+  // zero-padded shift: the per-sample softmax weights depend on x, Wq, Wk, scaling -> recompute them here and
+  // back-propagate through them after the cell phase
+  const bool zp = (m.flags & GNCA_F_GRAPH) && !(m.flags & GNCA_F_TORUS) && a.k > 0;
+  if (zp) {
+    int rc = run_attn_prepass(m, P, packed, a, fws, st);
+    if (rc) return rc;
+    GNCA_CHECK_CUDA(cudaMemsetAsync(w.attn.gw_part, 0, w.gw_bytes, st));
+  }
   BwdArgs A{};
   A.s = a;
+  A.gw_part = zp ? w.attn.gw_part : nullptr;
+  A.grow = zp ? w.attn.grow : nullptr;
+  A.zp_rowsum = zp ? fws.rowsum : nullptr;
+  A.zp_scratch = w.attn;
   A.gout = gout; A.gx = gx; A.u = a.u; A.stats = stats;
   A.actmask = w.actmask; A.postmask = w.postmask; A.gz = w.gz; A.gy = w.gy; A.gxs = w.gxs;
   A.tile_part = w.tile_part; A.sums = w.sums; A.wpart = w.wpart;
@@ -749,6 +804,6 @@ extern "C" int gnca_step_bwd(const gnca_model* m, const float* packed_dev, int B
   a.fire_u = fire_u_dev;
   a.x_in = x_in_dev; a.u = const_cast<float*>(u_dev);
   const Packed P = make_packed(m->C, m->hidden, m->d_model, graph);
-  return run_step_bwd(*m, P, packed_dev, a, stats_dev, gout_dev, gx_dev, gparams_dev,
+  return run_step_bwd(*m, P, packed_dev, a, stats_dev, gout_dev, gx_dev, gparams_dev, fws,
                       reinterpret_cast<char*>(workspace_dev) + fws.bytes, true, true, (cudaStream_t)stream);
 }

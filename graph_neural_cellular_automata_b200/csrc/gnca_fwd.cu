@@ -145,6 +145,19 @@ __global__ void k_attn_weights(StepArgs a, Packed P, int C, int d, const float* 
   }
 }
 
+// rowsum + per-sample softmax weights of the zero-padded shift; leaves a.attn_w pointing at ws.attn_w
+int run_attn_prepass(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const FwdWorkspace& ws,
+                     cudaStream_t st) {
+  const int rows = a.B * m.C * a.H;
+  k_rowsum<<<(rows + 7) / 8, 256, 0, st>>>(rows, a.W, a.x_in, ws.rowsum);
+  GNCA_LAUNCH_CHECK();
+  const size_t sm = (size_t)(2 * m.C + 2 * m.d_model + a.k + 4) * sizeof(float);
+  k_attn_weights<<<a.B, 128, sm, st>>>(a, P, m.C, m.d_model, packed, ws.rowsum, ws.attn_w);
+  GNCA_LAUNCH_CHECK();
+  a.attn_w = ws.attn_w;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_update
 // ------------------------------------------------------------------------------------------------
@@ -476,13 +489,8 @@ int launch_step_fwd(const gnca_model& m, const Packed& P, const float* packed, S
   a.partials = ws.partials;
   a.attn_w = nullptr;
   if (graph && !torus && a.k > 0) {   // per-sample softmax weights (zero-padded shift)
-    const int rows = a.B * C * a.H;
-    k_rowsum<<<(rows + 7) / 8, 256, 0, st>>>(rows, a.W, a.x_in, ws.rowsum);
-    GNCA_LAUNCH_CHECK();
-    const size_t sm = (size_t)(2 * C + 2 * m.d_model + a.k + 4) * sizeof(float);
-    k_attn_weights<<<a.B, 128, sm, st>>>(a, P, C, m.d_model, packed, ws.rowsum, ws.attn_w);
-    GNCA_LAUNCH_CHECK();
-    a.attn_w = ws.attn_w;
+    int rc = run_attn_prepass(m, P, packed, a, ws, st);
+    if (rc) return rc;
   }
   const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
   GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -506,6 +514,28 @@ int launch_step_fwd(const gnca_model& m, const Packed& P, const float* packed, S
     GNCA_LAUNCH_CHECK();
   }
   return 0;
+}
+
+template <int C>
+static int launch_attn_map(const Packed& P, const float* packed, StepArgs& a, const FwdWorkspace& ws, float* attn_out,
+                           cudaStream_t st) {
+  dim3 g3((a.H * a.W + 255) / 256, a.B);
+  k_absmean_msg<C><<<g3, 256, 0, st>>>(a, P, packed, ws.absmean);
+  GNCA_LAUNCH_CHECK();
+  k_attn_map<<<a.B, 256, 0, st>>>(a, ws.absmean, attn_out);
+  GNCA_LAUNCH_CHECK();
+  return 0;
+}
+
+int run_attn_map(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const FwdWorkspace& ws,
+                 float* attn_out, cudaStream_t st) {
+  switch (m.C) {
+    case 4: return launch_attn_map<4>(P, packed, a, ws, attn_out, st);
+    case 8: return launch_attn_map<8>(P, packed, a, ws, attn_out, st);
+    case 16: return launch_attn_map<16>(P, packed, a, ws, attn_out, st);
+    case 32: return launch_attn_map<32>(P, packed, a, ws, attn_out, st);
+  }
+  return GNCA_ERR_UNSUPPORTED;
 }
 
 int dispatch_step_fwd(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const FwdWorkspace& ws,
@@ -547,13 +577,8 @@ int launch_step_recompute(const gnca_model& m, const Packed& P, const float* pac
   a.partials = ws.partials;
   a.attn_w = nullptr;
   if (graph && !(m.flags & GNCA_F_TORUS) && a.k > 0) {
-    const int rows = a.B * C * a.H;
-    k_rowsum<<<(rows + 7) / 8, 256, 0, st>>>(rows, a.W, a.x_in, ws.rowsum);
-    GNCA_LAUNCH_CHECK();
-    const size_t sm = (size_t)(2 * C + 2 * m.d_model + a.k + 4) * sizeof(float);
-    k_attn_weights<<<a.B, 128, sm, st>>>(a, P, C, m.d_model, packed, ws.rowsum, ws.attn_w);
-    GNCA_LAUNCH_CHECK();
-    a.attn_w = ws.attn_w;
+    int rc = run_attn_prepass(m, P, packed, a, ws, st);
+    if (rc) return rc;
   }
   const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
   GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -648,7 +673,9 @@ int gnca_pack_weights(const gnca_model* m, const float* params_dev, float* packe
 size_t gnca_step_workspace_bytes(const gnca_model* m, int B, int H, int W) {
   if (!m || B <= 0 || H <= 0 || W <= 0) return 0;
   // forward part + backward part (see gnca_bwd.cu); the backward carve starts after the forward one
-  return carve_fwd_workspace(nullptr, *m, B, H, W).bytes + bwd_workspace_bytes(*m, B, H, W);
+  const size_t bw = bwd_workspace_bytes(*m, B, H, W);
+  const size_t gw = (m->flags & GNCA_F_GRAPH) ? graph_workspace_bytes(*m, B, H, W) : 0;
+  return carve_fwd_workspace(nullptr, *m, B, H, W).bytes + (bw > gw ? bw : gw);
 }
 
 int gnca_step_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const float* x_in_dev,

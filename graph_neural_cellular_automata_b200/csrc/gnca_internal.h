@@ -22,13 +22,31 @@ int dispatch_step_fwd(const gnca_model& m, const Packed& P, const float* packed,
 int dispatch_step_recompute(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a,
                             const FwdWorkspace& ws, cudaStream_t st);
 
+int run_attn_prepass(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const FwdWorkspace& ws,
+                     cudaStream_t st);
+int run_attn_map(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const FwdWorkspace& ws,
+                 float* attn_out, cudaStream_t st);
+// zero-padded-shift attention backward (gnca_graph.cu): softmax / logits / pooled Q,K -> gparams (wq,bq,wk,bk,
+// scaling) and the per-(b,c,row) additive term `grow` of dL/dx.  gw_part: [B][nparts][k] partial sums of
+// dL/dw_i; rowsum / a.attn_w from run_attn_prepass on the same x.
+struct AttnBwdScratch {
+  float* gw_part;   // [B][nparts][GNCA_MAX_K]
+  float* grow;      // [B][C][H]
+  float* pw;        // [B][2*d*C + 2*d + 1]
+};
+size_t attn_bwd_scratch_bytes(const gnca_model& m, int B, int H, int nparts);
+AttnBwdScratch carve_attn_bwd(void* base, const gnca_model& m, int B, int H, int nparts);
+int run_attn_bwd(const gnca_model& m, const Packed& P, const float* packed, const StepArgs& a, const float* rowsum,
+                 const AttnBwdScratch& sc, int nparts, float* gparams, cudaStream_t st);
+
+size_t graph_workspace_bytes(const gnca_model& m, int B, int H, int W);
 size_t bwd_workspace_bytes(const gnca_model& m, int B, int H, int W);
 // Backward of one step.  `a` describes the step (x_in, u, schedule...).  Weight-gradient partials live in the
 // workspace: zero_partials clears them first, reduce_partials folds them into gparams at the end (a rollout
 // clears at its first step and reduces after its last).
 int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, const StepArgs& a, const float* stats,
-                 const float* gout, float* gx, float* gparams, void* bwd_ws, bool zero_partials, bool reduce_partials,
-                 cudaStream_t st);
+                 const float* gout, float* gx, float* gparams, const FwdWorkspace& fws, void* bwd_ws, bool zero_partials,
+                 bool reduce_partials, cudaStream_t st);
 
 // cluster-resident forward rollout (gnca_resident.cu); GNCA_ERR_UNSUPPORTED when the configuration has no
 // resident kernel (zero-padded graph shift, sample too large for the cluster's shared memory)

@@ -160,7 +160,7 @@ int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H,
     int rc = dispatch_step_recompute(*m, P, packed_dev, a, fws, st);
     if (rc) return rc;
     float* gnext = (t == 0) ? g0_dev : (((T - 1 - t) & 1) ? r.g_b : r.g_a);
-    rc = run_step_bwd(*m, P, packed_dev, a, r.stats, gcur, gnext, gparams_dev, bws, t == T - 1, t == 0, st);
+    rc = run_step_bwd(*m, P, packed_dev, a, r.stats, gcur, gnext, gparams_dev, fws, bws, t == T - 1, t == 0, st);
     if (rc) return rc;
     if (sched->damage && t == sched->damage_step) {
       k_mul_inplace<<<(int)((N + 1023) / 1024 < 2368 ? (N + 1023) / 1024 : 2368), 256, 0, st>>>(N, gnext, sched->damage);
@@ -169,22 +169,6 @@ int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H,
     gcur = gnext;
   }
   return 0;
-}
-
-int gnca_graph_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const float* x_dev,
-                   const int32_t* offsets_host, int k, float* msg_dev, float* attn_dev, void* workspace_dev,
-                   size_t workspace_bytes, void* stream) {
-  (void)m; (void)packed_dev; (void)B; (void)H; (void)W; (void)x_dev; (void)offsets_host; (void)k; (void)msg_dev;
-  (void)attn_dev; (void)workspace_dev; (void)workspace_bytes; (void)stream;
-  return GNCA_ERR_UNSUPPORTED;
-}
-
-int gnca_graph_bwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const float* x_dev,
-                   const int32_t* offsets_host, int k, const float* gmsg_dev, float* gx_dev, float* gparams_dev,
-                   void* workspace_dev, size_t workspace_bytes, void* stream) {
-  (void)m; (void)packed_dev; (void)B; (void)H; (void)W; (void)x_dev; (void)offsets_host; (void)k; (void)gmsg_dev;
-  (void)gx_dev; (void)gparams_dev; (void)workspace_dev; (void)workspace_bytes; (void)stream;
-  return GNCA_ERR_UNSUPPORTED;
 }
 
 }  // extern "C"

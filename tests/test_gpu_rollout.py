@@ -73,16 +73,16 @@ def test_rollout_equals_sequential_steps(impl):
 
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("fname,kind", [("graph_torus_grads.npz", "graph"), ("graph_torus_grads_ragged.npz", "graph"),
-                                        ("classic_grads.npz", "classic")])
+                                        ("classic_grads.npz", "classic"), ("graph_zeropad_grads.npz", "zeropad")])
 def test_rollout_grads_golden(impl, fname, kind):
     g = load_golden(fname)
-    m = graph_model(True) if kind == "graph" else classic_model()
+    m = graph_model(True) if kind == "graph" else (graph_model(False) if kind == "zeropad" else classic_model())
     T = len(g["gains"])
     B = g["x0"].shape[0]
     x0 = T32(g["x0"]).to(DEV).requires_grad_(True)
     steps = g["steps"].tolist() if "steps" in g else None
     sched = make_schedule(m, B, 40, 40, T, fire_rate=g["fire_rates"].tolist(),
-                          offsets=[tup(c) for c in g["chosen"]] if kind == "graph" else None,
+                          offsets=[tup(c) for c in g["chosen"]] if kind != "classic" else None,
                           fire_u=T32(g["fire_u"]).to(DEV), message_gains=g["gains"].tolist(), steps=steps)
     target = T32(np.load(os.path.join(GOLDEN, "target_gecko_surrogate.npy"))).to(DEV)
     xT = _supported(impl, lambda: rollout(m, x0, sched, impl=impl))
@@ -101,6 +101,8 @@ def test_rollout_grads_golden(impl, fname, kind):
         ours = named[name].grad if named[name].grad is not None else torch.zeros_like(named[name])
         if kind == "graph" and any(s in name for s in ("query_proj", "key_proj", "scaling")):
             assert float(ours.abs().max()) <= 1e-8, name
+        elif kind == "zeropad" and any(s in name for s in ("query_proj", "key_proj", "scaling")):
+            assert rel_err(ours.cpu(), v) < 1e-3, (name, rel_err(ours.cpu(), v))   # tiny (~1e-3) second-order path
         else:
             assert rel_err(ours.cpu(), v) < 1e-4, (name, rel_err(ours.cpu(), v))
 

@@ -218,3 +218,45 @@ def test_rejects_cpu_and_wrong_dtype():
         m(torch.zeros(1, 16, 40, 40), fire_rate=1.0)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 16, 40, 40, device=DEV, dtype=torch.float64), fire_rate=1.0)
+
+
+def test_grads_graph_zeropad():
+    """Module default (zero-padded shift): real gradients flow to query/key/scaling through the softmax weights."""
+    _grad_case("graph_zeropad_grads.npz", graph_model(False), False)
+
+
+@pytest.mark.parametrize("torus", [True, False])
+def test_graph_augmentation_operator(torus):
+    """GraphAugmentation.forward stand-alone (message + attention map) and its backward vs the oracle."""
+    g = load_golden(f"graph_{'torus' if torus else 'zeropad'}_step.npz")
+    m = graph_model(torus)
+    x = T32(g["x_in"]).to(DEV).requires_grad_(True)
+    chosen = tup(g["chosen_graph"])
+    from graph_neural_cellular_automata_b200 import graph_ops
+    msg, attn = graph_ops.graph_message(m.graph, x, chosen, True)
+    assert max_rel(msg.detach().cpu(), g["graph_m"]) < 1e-5
+    assert max_rel(attn.cpu(), g["graph_attn"], floor=1e-2) < 1e-4
+    # forward() draws its own offsets from python's RNG exactly once
+    random.seed(77)
+    out = m.graph(x.detach())
+    random.seed(77)
+    ch = random.sample(m.graph.offsets, 8)
+    ref = O.graph_message(x.detach().cpu(), load_params("weights_graph_ep960.npz"), ch, ocfg(torus))
+    assert max_rel(out.cpu(), ref) < 1e-5
+    # backward
+    w = torch.randn_like(msg)
+    (msg * w).sum().backward()
+    p = {k: v.clone().requires_grad_(k.startswith("graph.") and "gate_mlp" not in k)
+         for k, v in load_params("weights_graph_ep960.npz").items()}
+    xo = x.detach().cpu().clone().requires_grad_(True)
+    (O.graph_message(xo, p, chosen, ocfg(torus)) * w.cpu()).sum().backward()
+    assert rel_err(x.grad.cpu(), xo.grad) < 1e-4
+    named = dict(m.named_parameters())
+    for k in ("graph.msg_proj.weight", "graph.msg_proj.bias"):
+        assert rel_err(named[k].grad.cpu(), p[k].grad) < 1e-4, k
+    for k in ("graph.query_proj.weight", "graph.query_proj.bias", "graph.key_proj.weight", "graph.key_proj.bias",
+              "graph.scaling"):
+        if torus:
+            assert float(named[k].grad.abs().max()) <= 1e-8
+        else:
+            assert rel_err(named[k].grad.cpu(), p[k].grad) < 1e-3, (k, rel_err(named[k].grad.cpu(), p[k].grad))
