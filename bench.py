@@ -223,6 +223,12 @@ def main():
         target = torch.from_numpy(np.load(os.path.join(GOLDEN, "target_gecko_surrogate.npy"))).to(dev)
 
     def make_x0():
+        if C_ == 16 and cfg["train"]:       # pool-like states: seeds grown for a random number of steps
+            x = make_seed(C_, H, B, device=dev)
+            with torch.no_grad():
+                for t in range(48):
+                    x = model(x, fire_rate=0.6)
+            return x.cpu()
         if C_ == 16:
             return make_seed(C_, H, B, device="cpu")
         x = torch.rand(B, C_, H, W)
@@ -236,15 +242,23 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
     updates = B * T * H * W
 
+    if cfg["train"]:
+        from graph_neural_cellular_automata_b200.training.trainer import premult_loss
+        from graph_neural_cellular_automata_b200.training.optim import FusedNormalizedAdam
+        from graph_neural_cellular_automata_b200.rollout import rollout_fwd_raw, rollout_bwd_raw
+        opt = FusedNormalizedAdam(model, lr=2e-4, weight_decay=1e-5, normalize=True)
+        IMPLN = {"auto": 0, "streaming": 1, "resident": 2}[args.rollout_impl]
+
     def one_rollout(x0, sched):
-        if cfg["train"]:
-            xT = rollout(model, x0, sched, impl=args.rollout_impl)
-            pred = xT[:, :4]
-            rgba = torch.cat([pred[:, :3] * pred[:, 3:4], pred[:, 3:4]], 1)
-            loss = ((rgba - target.unsqueeze(0)) ** 2).mean()
-            model.zero_grad(set_to_none=True)
-            loss.backward()
-            return xT.detach()
+        if cfg["train"]:     # fwd (history) + premult loss + BPTT + grad normalise + Adam: one training iteration's hot path
+            desc, packed = model.model_desc(), model.packed_weights()
+            xT, hist = rollout_fwd_raw(desc, packed, x0, sched, history=True, impl=IMPLN)
+            per, gxT = premult_loss(xT, target, 1.0 / (B * world))
+            _, gflat = rollout_bwd_raw(desc, packed, hist, sched, gxT, impl=IMPLN)
+            if world > 1:
+                dist.all_reduce(gflat)
+            opt.step(gflat)
+            return xT
         with torch.no_grad():
             return rollout(model, x0, sched, impl=args.rollout_impl)
 
