@@ -182,9 +182,15 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--rollout-impl", default="auto", choices=["auto", "streaming", "resident"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--T", type=int, default=0, help="development: override the number of CA steps per rollout")
+    ap.add_argument("--B", type=int, default=0, help="development: override the per-GPU batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = workload_cfg(args.workload)
+    if args.T > 0:
+        cfg["T"] = args.T
+    if args.B > 0:
+        cfg["B"] = args.B
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -42,6 +42,7 @@ struct ResidentArgs {
   int damage_step;
   unsigned long long* dbg;    // optional phase-cycle counters (GNCA_PHASE_TIMING=<cta index>), else null
   int dbg_cta;
+  int dbg_repeat;             // development: bitmask of phases to execute twice (idempotent; cost = time delta)
   int dbg_skip;               // development: bitmask of phases to skip (timing experiments only; results wrong)
 };
 
@@ -55,9 +56,13 @@ struct ResidentArgs {
     }                                                                               \
   } while (0)
 
-// cluster barrier with cluster-scope release/acquire (cooperative_groups' cluster.sync() fences at GPU scope)
+// Cluster barrier.  The arrive is a release (every DSMEM store issued before it is performed before a peer
+// passes the wait); the wait carries NO acquire: an acquire makes ptxas emit CCTL.IVALL, which invalidates the
+// whole L1 -- including the lines backing local memory (stack) -- at every barrier.  Nothing exchanged inside the
+// kernel travels through L1-cached global memory (peers communicate through shared::cluster stores only), so the
+// invalidation buys nothing here.
 __device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.aligned;\n" ::: "memory");
 }
 
 // Out-of-line helpers: the per-step code of the resident kernel has to stay small enough for the instruction
@@ -136,8 +141,8 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
   float* s_fr = reinterpret_cast<float*>(s_ox + ((nown + 15) & ~15));      // [T] fire rate per step
   float* s_gain = s_fr + R.T;                                               // [T] message gain per step
   signed char* s_off = reinterpret_cast<signed char*>(s_gain + R.T);        // [T][k][2] offsets
-  __shared__ double s_parts[8][2];           // (sum u, sum u^2) of every CTA of the cluster, pushed by its owner
-  __shared__ double s_wred[kRWarps][2];
+  __shared__ float s_partsf[8][2];           // (sum u, sum u^2) of every CTA of the cluster, pushed by its owner
+  __shared__ float s_wredf[kRWarps][2];
   __shared__ float s_sc[C], s_bi[C], s_idle[C], s_gam[C], s_bet[C], s_stat[2];
   __shared__ int s_wcount[kRWarps], s_wbase[kRWarps + 1];
   __shared__ unsigned long long s_dbg[16];
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
     const bool msg_on = graph && gain_m != 0.f && a.k > 0;
 
     // ---- P1: alive & fire on own cells, deterministic compaction ------------------------------------------
-    {
+    for (int rep_ = 0; rep_ < ((R.dbg_repeat & 8) ? 2 : 1); ++rep_) {
       int cnt = 0;
       const int per = ((nown + kRThreads - 1) / kRThreads) * 32;     // own cells per warp (multiple of 32)
       const int lo = warp * per;
@@ -279,35 +284,41 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
     float ps1 = 0.f, ps2 = 0.f;
     for (int base = 0; base < ((R.dbg_skip & 1) ? 0 : nact); base += MB) {
       const int nb = min(MB, nact - base);
-      const int G = nb > 32 ? 8 : 4;                    // cells per warp tile in layer 1
+      const int G = nb > 32 ? 8 : 4;                    // cells per warp tile (layer 1 + layer 2 stay inside one warp)
       const int nbp = ((nb + G - 1) / G) * G;           // staged cells (zero padded to the tile)
-      // 2a/2b: one half-warp per cell: perception of its C channels, sender table, gathered sender state
-      {
+      // 2a: sender table, one lane per (cell, offset): local index of the (alive) sender or -1
+      for (int rep_ = 0; rep_ < ((R.dbg_repeat & 1) ? 2 : 1); ++rep_) {
+        if (msg_on) {
+          for (int i = tid; i < nb * a.k; i += kRThreads) {
+            const int cl = i / a.k, oi = i - cl * a.k;
+            const int oc = s_actlist[base + cl];
+            const int orow = s_oy[oc], x = s_ox[oc], gy = r0 + orow;
+            const int dy = s_off[(t * a.k + oi) * 2], dx = s_off[(t * a.k + oi) * 2 + 1];
+            int gq = (gy - dy) % H; gq = gq < 0 ? gq + H : gq;       // sender's global row (torus)
+            int qx = (x - dx) % W; qx = qx < 0 ? qx + W : qx;
+            const int lq = HALO + orow - dy;                          // its local row (halo holds the wrap)
+            int q = lq * W + qx;
+            if (a2a && !alive_local(sA, lq, qx, gq, a.graph_alpha_thr)) q = -1;
+            s_q[cl * kk + oi] = q;
+          }
+          __syncthreads();
+        }
+        // 2b: one half-warp per cell, lane = channel: perception (9 independent loads) and the gathered sender
+        //     state xs = sum_i w x(q_i) with the k loads issued back to back (invalid senders get weight 0)
         const int hw = tid >> 4, l16 = tid & 15;
-        for (int cl = hw; cl < nbp; cl += kRThreads / 16) {      // nbp is even: both halves of a warp iterate alike
+        const float wuni = a.k > 0 ? 1.0f / (float)a.k : 0.f;
+        for (int cl = hw; cl < nbp; cl += kRThreads / 16) {
           const bool valid = cl < nb;
           int orow = 0, x = 0;
           if (valid) { const int oc = s_actlist[base + cl]; orow = s_oy[oc]; x = s_ox[oc]; }
           const int gy = r0 + orow;
-          if (msg_on) {
-            if (valid) {
-              for (int oi = l16; oi < a.k; oi += 16) {
-                const int dy = s_off[(t * a.k + oi) * 2], dx = s_off[(t * a.k + oi) * 2 + 1];
-                int gq = (gy - dy) % H; gq = gq < 0 ? gq + H : gq;       // sender's global row (torus)
-                int qx = (x - dx) % W; qx = qx < 0 ? qx + W : qx;
-                const int lq = HALO + orow - dy;                          // its local row (halo holds the wrap)
-                int q = lq * W + qx;
-                if (a2a && !alive_local(sA, lq, qx, gq, a.graph_alpha_thr)) q = -1;
-                s_q[cl * kk + oi] = q;
-              }
-            }
-            __syncwarp();
-          }
           const bool up = gy > 0, dn = gy < H - 1, lf = x > 0, rt = x < W - 1;
+          int nvalid = 0;
           for (int c = l16; c < C; c += 16) {
             float vid = 0.f, vsx = 0.f, vsy = 0.f, xs = 0.f;
             if (valid) {
-              const float* p = sX + (size_t)c * PL + (HALO + orow) * W + x;
+              const float* pc = sX + (size_t)c * PL;
+              const float* p = pc + (HALO + orow) * W + x;
               const float a00 = (up && lf) ? p[-W - 1] : 0.f, a01 = up ? p[-W] : 0.f, a02 = (up && rt) ? p[-W + 1] : 0.f;
               const float a10 = lf ? p[-1] : 0.f, a12 = rt ? p[1] : 0.f;
               const float a20 = (dn && lf) ? p[W - 1] : 0.f, a21 = dn ? p[W] : 0.f, a22 = (dn && rt) ? p[W + 1] : 0.f;
@@ -315,10 +326,25 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
               vsx = (a00 - a02) + 2.f * (a10 - a12) + (a20 - a22);
               vsy = (a00 + 2.f * a01 + a02) - (a20 + 2.f * a21 + a22);
               if (msg_on) {
-                const float wuni = 1.0f / (float)a.k;
-                for (int oi = 0; oi < a.k; ++oi) {
-                  const int q = s_q[cl * kk + oi];
-                  if (q >= 0) xs = fmaf(wuni, sX[(size_t)c * PL + q], xs);
+                nvalid = 0;
+                const int* qrow = s_q + cl * kk;
+                for (int o4 = 0; o4 < a.k; o4 += 4) {
+                  int q0, q1, q2, q3;
+                  if ((kk & 3) == 0) {
+                    const int4 qq = *reinterpret_cast<const int4*>(qrow + o4);
+                    q0 = qq.x; q1 = qq.y; q2 = qq.z; q3 = qq.w;
+                  } else {
+                    q0 = qrow[o4];
+                    q1 = (o4 + 1 < a.k) ? qrow[o4 + 1] : -1;
+                    q2 = (o4 + 2 < a.k) ? qrow[o4 + 2] : -1;
+                    q3 = (o4 + 3 < a.k) ? qrow[o4 + 3] : -1;
+                  }
+                  const float v0 = pc[max(q0, 0)], v1 = pc[max(q1, 0)], v2 = pc[max(q2, 0)], v3 = pc[max(q3, 0)];
+                  xs = fmaf(q0 >= 0 ? wuni : 0.f, v0, xs);
+                  xs = fmaf(q1 >= 0 ? wuni : 0.f, v1, xs);
+                  xs = fmaf(q2 >= 0 ? wuni : 0.f, v2, xs);
+                  xs = fmaf(q3 >= 0 ? wuni : 0.f, v3, xs);
+                  nvalid += (q0 >= 0) + (q1 >= 0) + (q2 >= 0) + (q3 >= 0);
                 }
               }
             }
@@ -329,143 +355,151 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
           }
           if (l16 == 0) {
             float as = 0.f;
-            if (valid && msg_on) {
-              const float wuni = 1.0f / (float)a.k;
-              for (int oi = 0; oi < a.k; ++oi) if (s_q[cl * kk + oi] >= 0) as += wuni;
-            }
+            for (int n = 0; n < nvalid; ++n) as += wuni;     // same summation as the streaming path
             AS[cl] = as;
           }
+          __syncwarp();     // nbp is even: both half-warps of a warp run this loop the same number of times
+          // message projection by the first CQ lanes of the half-warp:
+          //   MSGt[c][cl] = gain * tanh(bm[c]*as + sum_ci Wm[c][ci] xs[ci]) on the gated channels, else 0
+          if (l16 < CQ) {
+            const int cq = l16;
+            float agg[4] = {0.f, 0.f, 0.f, 0.f};
+            if (msg_on && valid && 4 * cq + 3 >= c_lo) {
+              const float as = AS[cl];
+              const float4 bmv = *reinterpret_cast<const float4*>(sbm + 4 * cq);
+              agg[0] = bmv.x * as; agg[1] = bmv.y * as; agg[2] = bmv.z * as; agg[3] = bmv.w * as;
+#pragma unroll 4
+              for (int ci = 0; ci < C; ++ci) {
+                const float xv = XSt[ci * MBP + cl];
+                const float4 w = *reinterpret_cast<const float4*>(sWmT + ci * C + 4 * cq);
+                agg[0] = fmaf(w.x, xv, agg[0]); agg[1] = fmaf(w.y, xv, agg[1]);
+                agg[2] = fmaf(w.z, xv, agg[2]); agg[3] = fmaf(w.w, xv, agg[3]);
+              }
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) agg[cc] = (4 * cq + cc >= c_lo) ? tanhf(agg[cc]) * gain_m : 0.f;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) MSGt[(4 * cq + cc) * MBP + cl] = agg[cc];
+          }
         }
+        if (rep_ == 0 && (R.dbg_repeat & 1)) __syncthreads();
       }
       __syncthreads();
       GNCA_PHASE_MARK(10);
-      // message projection: MSGt[c][cl] = gain * tanh(bm[c]*as + sum_ci Wm[c][ci] xs[ci]) on gated channels
-      for (int i = tid; i < nb * CQ; i += kRThreads) {
-        const int cq = i & (CQ - 1), cl = i >> LCQ;
-        float agg[4] = {0.f, 0.f, 0.f, 0.f};
-        if (msg_on && 4 * cq + 3 >= c_lo) {
-          const float as = AS[cl];
-          const float4 bmv = *reinterpret_cast<const float4*>(sbm + 4 * cq);
-          agg[0] = bmv.x * as; agg[1] = bmv.y * as; agg[2] = bmv.z * as; agg[3] = bmv.w * as;
-#pragma unroll 4
-          for (int ci = 0; ci < C; ++ci) {
-            const float xv = XSt[ci * MBP + cl];
-            const float4 w = *reinterpret_cast<const float4*>(sWmT + ci * C + 4 * cq);
-            agg[0] = fmaf(w.x, xv, agg[0]); agg[1] = fmaf(w.y, xv, agg[1]);
-            agg[2] = fmaf(w.z, xv, agg[2]); agg[3] = fmaf(w.w, xv, agg[3]);
-          }
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) agg[cc] = (4 * cq + cc >= c_lo) ? tanh_ool(agg[cc]) * gain_m : 0.f;
-        }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) MSGt[(4 * cq + cc) * MBP + cl] = agg[cc];
-      }
-      // 2c: layer 1.  warp = tile of G cells, lane = 4 (permuted) hidden units per 128-group
-      auto layer1 = [&](auto gtag) {
+      // 2c: layer 1 + layer 2 inside ONE warp per tile of G cells (no block barrier in between): lane = 4 permuted
+      //     hidden units for layer 1; for layer 2 the warp re-reads its own h columns with the hidden dimension
+      //     split over 4 lane groups (j = 4*jj + kq) and reduces with two shuffle levels.
+      auto mlp_tile = [&](auto gtag) {
         constexpr int GG = decltype(gtag)::value;
         const int ngroups = nbp / GG;
-        for (int item = warp; item < ngroups * JG; item += kRWarps) {
-          const int cgp = item % ngroups, g = item / ngroups;
-          const int jp = g * 128 + lane * 4;            // permuted index of this lane's 4 units
-          float acc[GG][4];
-          const float4 bb = *reinterpret_cast<const float4*>(sb1 + jp);
+        for (int cgp = warp; cgp < ngroups; cgp += kRWarps) {
+          const int jp = lane * 4;                      // permuted index of this lane's 4 hidden units
+          {
+            float acc[GG][4];
+            const float4 bb = *reinterpret_cast<const float4*>(sb1 + jp);
 #pragma unroll
-          for (int m = 0; m < GG; ++m) { acc[m][0] = bb.x; acc[m][1] = bb.y; acc[m][2] = bb.z; acc[m][3] = bb.w; }
+            for (int m = 0; m < GG; ++m) { acc[m][0] = bb.x; acc[m][1] = bb.y; acc[m][2] = bb.z; acc[m][3] = bb.w; }
 #pragma unroll 4
-          for (int k = 0; k < C3; ++k) {
-            const float4 w = *reinterpret_cast<const float4*>(sW1T + k * hid + jp);
-            float ym[GG];
+            for (int k = 0; k < C3; ++k) {
+              const float4 w = *reinterpret_cast<const float4*>(sW1T + k * hid + jp);
+              float ym[GG];
 #pragma unroll
-            for (int m4 = 0; m4 < GG / 4; ++m4) {
-              const float4 yv = *reinterpret_cast<const float4*>(Yt + k * MBP + GG * cgp + 4 * m4);
-              ym[4 * m4] = yv.x; ym[4 * m4 + 1] = yv.y; ym[4 * m4 + 2] = yv.z; ym[4 * m4 + 3] = yv.w;
+              for (int m4 = 0; m4 < GG / 4; ++m4) {
+                const float4 yv = *reinterpret_cast<const float4*>(Yt + k * MBP + GG * cgp + 4 * m4);
+                ym[4 * m4] = yv.x; ym[4 * m4 + 1] = yv.y; ym[4 * m4 + 2] = yv.z; ym[4 * m4 + 3] = yv.w;
+              }
+#pragma unroll
+              for (int m = 0; m < GG; ++m) {
+                acc[m][0] = fmaf(ym[m], w.x, acc[m][0]); acc[m][1] = fmaf(ym[m], w.y, acc[m][1]);
+                acc[m][2] = fmaf(ym[m], w.z, acc[m][2]); acc[m][3] = fmaf(ym[m], w.w, acc[m][3]);
+              }
             }
 #pragma unroll
-            for (int m = 0; m < GG; ++m) {
-              acc[m][0] = fmaf(ym[m], w.x, acc[m][0]); acc[m][1] = fmaf(ym[m], w.y, acc[m][1]);
-              acc[m][2] = fmaf(ym[m], w.z, acc[m][2]); acc[m][3] = fmaf(ym[m], w.w, acc[m][3]);
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = lane + 32 * jj;             // true hidden index (row of Ht / W2T)
+#pragma unroll
+              for (int m4 = 0; m4 < GG / 4; ++m4) {
+                float4 hv;
+                hv.x = fmaxf(acc[4 * m4][jj], 0.f); hv.y = fmaxf(acc[4 * m4 + 1][jj], 0.f);
+                hv.z = fmaxf(acc[4 * m4 + 2][jj], 0.f); hv.w = fmaxf(acc[4 * m4 + 3][jj], 0.f);
+                *reinterpret_cast<float4*>(Ht + j * MBP + GG * cgp + 4 * m4) = hv;
+              }
             }
           }
+          __syncwarp();
+          const int kq = lane >> 3, tl = lane & 7;
+          constexpr int NSUB = (GG / 2) * CQ;           // sub-tiles of 2 cells x 4 channels
+#pragma unroll 1
+          for (int st0 = 0; st0 < NSUB; st0 += 8) {
+            const int st = st0 + tl;
+            const bool on = st < NSUB;
+            const int cp = on ? st % (GG / 2) : 0, cq = on ? st / (GG / 2) : 0;
+            float o2[2][4];
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = g * 128 + lane + 32 * jj;     // true hidden index (row of Ht / W2T)
+            for (int m = 0; m < 2; ++m)
 #pragma unroll
-            for (int m4 = 0; m4 < GG / 4; ++m4) {
-              float4 hv;
-              hv.x = fmaxf(acc[4 * m4][jj], 0.f); hv.y = fmaxf(acc[4 * m4 + 1][jj], 0.f);
-              hv.z = fmaxf(acc[4 * m4 + 2][jj], 0.f); hv.w = fmaxf(acc[4 * m4 + 3][jj], 0.f);
-              *reinterpret_cast<float4*>(Ht + j * MBP + GG * cgp + 4 * m4) = hv;
+              for (int cc = 0; cc < 4; ++cc) o2[m][cc] = 0.f;
+#pragma unroll 4
+            for (int jj = 0; jj < 32; ++jj) {
+              const int j = 4 * jj + kq;
+              const float2 hv = *reinterpret_cast<const float2*>(Ht + j * MBP + GG * cgp + 2 * cp);
+              const float4 w = *reinterpret_cast<const float4*>(sW2T + j * C + 4 * cq);
+              o2[0][0] = fmaf(hv.x, w.x, o2[0][0]); o2[0][1] = fmaf(hv.x, w.y, o2[0][1]);
+              o2[0][2] = fmaf(hv.x, w.z, o2[0][2]); o2[0][3] = fmaf(hv.x, w.w, o2[0][3]);
+              o2[1][0] = fmaf(hv.y, w.x, o2[1][0]); o2[1][1] = fmaf(hv.y, w.y, o2[1][1]);
+              o2[1][2] = fmaf(hv.y, w.z, o2[1][2]); o2[1][3] = fmaf(hv.y, w.w, o2[1][3]);
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                float v = o2[m][cc];
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                o2[m][cc] = v;
+              }
+            if (on && kq == 0) {
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                const int cl = GG * cgp + 2 * cp + m;
+                if (cl < nb) {
+#pragma unroll
+                  for (int cc = 0; cc < 4; ++cc) {
+                    const int c = 4 * cq + cc;
+                    const float v = o2[m][cc] + MSGt[c * MBP + cl];
+                    Ut[(size_t)c * nown + base + cl] = v;
+                    ps1 += v;
+                    ps2 = fmaf(v, v, ps2);
+                  }
+                }
+              }
             }
           }
+          __syncwarp();
         }
       };
-      if (G == 8) layer1(std::integral_constant<int, 8>{}); else layer1(std::integral_constant<int, 4>{});
-      __syncthreads();
-      GNCA_PHASE_MARK(11);
-      // 2d: layer 2: the hidden dimension is split in kRSlices slices (warp % kRSlices); the warps of one slice
-      //     share the (4 cells x 4 channels) tiles
-      {
-        const int ncg = (nb + 3) >> 2;
-        const int ntile = ncg * CQ;
-        const int ks = warp % kRSlices, tw = warp / kRSlices;
-        const int jper = hid / kRSlices;
-        const int j0 = ks * jper, j1 = j0 + jper;
-        for (int tile = tw * 32 + lane; tile < ntile; tile += 32 * (kRWarps / kRSlices)) {
-          const int cq = tile & (CQ - 1), cgp = tile >> LCQ;
-          float acc[4][4];
-#pragma unroll
-          for (int m = 0; m < 4; ++m)
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) acc[m][cc] = 0.f;
-#pragma unroll 4
-          for (int j = j0; j < j1; ++j) {
-            const float4 hv = *reinterpret_cast<const float4*>(Ht + j * MBP + 4 * cgp);
-            const float4 w = *reinterpret_cast<const float4*>(sW2T + j * C + 4 * cq);
-            const float hm[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              acc[m][0] = fmaf(hm[m], w.x, acc[m][0]); acc[m][1] = fmaf(hm[m], w.y, acc[m][1]);
-              acc[m][2] = fmaf(hm[m], w.z, acc[m][2]); acc[m][3] = fmaf(hm[m], w.w, acc[m][3]);
-            }
-          }
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            *reinterpret_cast<float4*>(RED + ((size_t)ks * C + 4 * cq + cc) * MB + 4 * cgp) =
-                make_float4(acc[0][cc], acc[1][cc], acc[2][cc], acc[3][cc]);
-        }
+      for (int rep_ = 0; rep_ < ((R.dbg_repeat & 2) ? 2 : 1); ++rep_) {
+        float sv1 = ps1, sv2 = ps2;
+        if (G == 8) mlp_tile(std::integral_constant<int, 8>{}); else mlp_tile(std::integral_constant<int, 4>{});
+        if (rep_ == 0 && (R.dbg_repeat & 2)) { ps1 = sv1; ps2 = sv2; }
       }
-      __syncthreads();
-      GNCA_PHASE_MARK(12);
-      {
-        const int nstrip = (nb + 31) >> 5;
-        for (int item = warp; item < nstrip * C; item += kRWarps) {
-          const int c = item & (C - 1), cl = (item / C) * 32 + lane;
-          if (cl < nb) {
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < kRSlices; ++w) v += RED[((size_t)w * C + c) * MB + cl];
-            v += MSGt[c * MBP + cl];
-            Ut[(size_t)c * nown + base + cl] = v;
-            ps1 += v;
-            ps2 = fmaf(v, v, ps2);
-          }
-        }
-      }
-      __syncthreads();
+      __syncthreads();     // staging buffers are reused by the next batch
     }
     GNCA_PHASE_MARK(1);
 
     // ---- GroupNorm(1,C) statistics over the whole sample: block partial -> DSMEM all-gather ----------------
     float mu = 0.f, rstd = 1.f;
+    for (int rep_ = 0; rep_ < ((R.dbg_repeat & 512) ? 2 : 1); ++rep_)
     if (gn && !(R.dbg_skip & 2)) {
+      // fp32 tree (warp shuffles -> 16 warps -> NC CTAs); every CTA reduces the same values in the same order
       const float f1 = warp_sum(ps1), f2 = warp_sum(ps2);
-      if (lane == 0) { s_wred[warp][0] = (double)f1; s_wred[warp][1] = (double)f2; }
+      if (lane == 0) { s_wredf[warp][0] = f1; s_wredf[warp][1] = f2; }
       __syncthreads();
       if (warp == 0) {
-        double t1 = lane < kRWarps ? s_wred[lane][0] : 0.0, t2 = lane < kRWarps ? s_wred[lane][1] : 0.0;
-        t1 = warp_sum_ool(t1); t2 = warp_sum_ool(t2);
+        float t1 = lane < kRWarps ? s_wredf[lane][0] : 0.f, t2 = lane < kRWarps ? s_wredf[lane][1] : 0.f;
+        t1 = warp_sum(t1); t2 = warp_sum(t2);
         if (lane < NC) {                       // push our partial into slot `rank` of every CTA (incl. ourselves)
-          double* dst = cluster.map_shared_rank(&s_parts[0][0], lane);
+          float* dst = cluster.map_shared_rank(&s_partsf[0][0], lane);
           dst[rank * 2] = t1; dst[rank * 2 + 1] = t2;
         }
       }
@@ -473,32 +507,22 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
       cluster_barrier();                                                      // barrier 1
       GNCA_PHASE_MARK(3);
       if (warp == 0) {
-        double t1 = 0.0, t2 = 0.0;
-        if (lane < NC) { t1 = s_parts[lane][0]; t2 = s_parts[lane][1]; }
-        // same butterfly in every CTA of the cluster => bit-identical statistics cluster-wide
-        GNCA_PHASE_MARK(13);
-        const double a1 = warp_sum_ool(t1), a2 = warp_sum_ool(t2);
-        GNCA_PHASE_MARK(14);
-        if (lane == 0) {
-          const double invn = R.inv_n;
-          const double m = a1 * invn;
-          double var = fma(a2, invn, -m * m);
-          if (var < 0.0) var = 0.0;
-          s_stat[0] = (float)m;
-          s_stat[1] = 1.0f / sqrtf((float)var + a.gn_eps);
-          if (rank == 0 && R.stats_hist) {
-            R.stats_hist[((size_t)t * a.B + b) * 2] = s_stat[0];
-            R.stats_hist[((size_t)t * a.B + b) * 2 + 1] = s_stat[1];
-          }
+        float t1 = 0.f, t2 = 0.f;
+        if (lane < NC) { t1 = s_partsf[lane][0]; t2 = s_partsf[lane][1]; }
+        const float a1 = warp_sum(t1), a2 = warp_sum(t2);
+        const float invn = (float)R.inv_n;
+        const float m_ = a1 * invn;
+        const float var = fmaxf(fmaf(a2, invn, -m_ * m_), 0.f);
+        const float r_ = 1.0f / sqrtf(var + a.gn_eps);
+        if (lane == 0 && rank == 0 && R.stats_hist) {
+          R.stats_hist[((size_t)t * a.B + b) * 2] = m_;
+          R.stats_hist[((size_t)t * a.B + b) * 2 + 1] = r_;
         }
-        __syncwarp();
-        GNCA_PHASE_MARK(15);
         if (lane < C) {                       // C <= 32: the same warp finishes the per-channel affine
-          const float m_ = s_stat[0], r_ = s_stat[1];
           const float sc = r_ * s_gam[lane];
           const float bi = s_bet[lane] - m_ * sc;
           s_sc[lane] = sc; s_bi[lane] = bi;
-          s_idle[lane] = tanh_ool(bi) * a.update_gain;
+          s_idle[lane] = tanhf(bi) * a.update_gain;
         }
       }
     } else if (tid < C) {
@@ -509,16 +533,15 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
     GNCA_PHASE_MARK(4);
 
     // ---- P3: bounded update in place (own cells); idle update of the halo copies; pre-gate alpha rows -------
+    // inactive own cells: x += idle_c (their masked pre-norm update is 0); lanes <-> consecutive cells
     for (int item = warp; item < ((R.dbg_skip & 4) ? 0 : ((nown + 31) >> 5) * CQ); item += kRWarps) {
       const int cq = item & (CQ - 1), oc = (item >> LCQ) * 32 + lane;
-      if (oc >= nown) continue;
-      const int slot = s_slot[oc];
+      if (oc >= nown || s_slot[oc] >= 0) continue;
       float* px = sX + (size_t)(4 * cq) * PL + HALO * W + oc;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const int c = 4 * cq + cc;
-        const float d = slot >= 0 ? tanh_ool(fmaf(Ut[(size_t)c * nown + slot], s_sc[c], s_bi[c])) * a.update_gain : s_idle[c];
-        const float v = px[(size_t)cc * PL] + d;
+        const float v = px[(size_t)cc * PL] + s_idle[c];
         if (c == 3) {
           sAt[W + oc] = v;                                   // rows 1..own of sAt
           const int orow = s_oy[oc];
@@ -529,20 +552,42 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
         }
       }
     }
+    // active cells: x += gain * tanh(gn(u)); one lane per (slot, channel), lanes <-> consecutive slots
+    for (int item = warp; item < ((R.dbg_skip & 4) ? 0 : ((nact + 31) >> 5) * C); item += kRWarps) {
+      const int c = item & (C - 1), sl = (item / C) * 32 + lane;
+      if (sl >= nact) continue;
+      const int oc = s_actlist[sl];
+      const float d = tanhf(fmaf(Ut[(size_t)c * nown + sl], s_sc[c], s_bi[c])) * a.update_gain;
+      float* px = sX + (size_t)c * PL + HALO * W + oc;
+      const float v = *px + d;
+      if (c == 3) {
+        sAt[W + oc] = v;
+        const int orow = s_oy[oc];
+        if (orow == 0) pAt[(own + 1) * W + oc] = v;
+        if (orow == own - 1) nAt[oc - (own - 1) * W] = v;
+      } else {
+        *px = v;
+      }
+    }
+    for (int rep_ = 0; rep_ < ((R.dbg_repeat & 256) ? 3 : 1); ++rep_)
     for (int item = warp; item < ((2 * HALO * W + 31) >> 5) * CQ; item += kRWarps) {   // halo cells, channels != 3
       const int cq = item & (CQ - 1), hc = (item >> LCQ) * 32 + lane;
       if (hc >= 2 * HALO * W) continue;
       const int off = hc < HALO * W ? hc : own * W + hc;                    // top halo | bottom halo
       float* px = sX + (size_t)(4 * cq) * PL + off;
+      const float sgn_ = (rep_ == 1) ? -1.f : 1.f;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc)
-        if (4 * cq + cc != 3) px[(size_t)cc * PL] += s_idle[4 * cq + cc];
+        if (4 * cq + cc != 3) px[(size_t)cc * PL] += sgn_ * s_idle[4 * cq + cc];
     }
     __syncthreads();
     GNCA_PHASE_MARK(5);
+    if (R.dbg_repeat & 32) cluster_barrier();
+    if (R.dbg_repeat & 64) { for (int q_ = 0; q_ < 10; ++q_) __syncthreads(); }
     if (!(R.dbg_skip & 16)) cluster_barrier();                                // barrier 2
     GNCA_PHASE_MARK(6);
     // ---- P4: post-alive gate on own cells; push gated alpha rows + active cells' channels to the halos -------
+    for (int rep_ = 0; rep_ < ((R.dbg_repeat & 16) ? 2 : 1); ++rep_)
     for (int oc = tid; oc < ((R.dbg_skip & 8) ? 0 : nown); oc += kRThreads) {
       const int orow = s_oy[oc], x = s_ox[oc];
       const bool post = alive_local(sAt, 1 + orow, x, r0 + orow, a.alpha_thr);
@@ -604,7 +649,7 @@ static int launch_resident(const gnca_model& m, const Packed& P, const float* pa
                            cudaStream_t st) {
   const bool graph = (m.flags & GNCA_F_GRAPH) != 0;
   const int H = R.s.H, W = R.s.W;
-  if (m.hidden % 128 != 0 || C < 4 || W > 255) return GNCA_ERR_UNSUPPORTED;
+  if (m.hidden != 128 || C < 4 || W > 255) return GNCA_ERR_UNSUPPORTED;   // layer 1 + 2 of a tile live in one warp: 32 lanes x 4 units
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -643,6 +688,7 @@ static int launch_resident(const gnca_model& m, const Packed& P, const float* pa
     R.NC = NC; R.own_rows = own; R.halo = halo; R.MB = MB; R.plane_stride = plane_stride_of(own, halo, W);
     R.inv_n = 1.0 / ((double)C * (double)H * (double)W);
     if (getenv("GNCA_SKIP")) R.dbg_skip = atoi(getenv("GNCA_SKIP"));
+    if (getenv("GNCA_REPEAT")) R.dbg_repeat = atoi(getenv("GNCA_REPEAT"));
     static unsigned long long* dbg_buf = nullptr;
     if (getenv("GNCA_PHASE_TIMING")) {
       if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
