@@ -18,6 +18,7 @@ namespace gnca {
 
 constexpr int kBThreads = 256;
 constexpr int kBChunk = 1024;
+constexpr int kBChunkSmall = 256;
 constexpr int kBTileW = 32, kBTileH = 8;
 constexpr int kMaxBwdBlocks = 148;
 
@@ -47,7 +48,7 @@ struct BwdArgs {
   double* tile_part;        // [B][ntiles][2+2C]
   float* sums;              // [B][2]  S1/N, S2/N
   float* wpart;             // [nblocks][canonical total]
-  int ntiles, nblocks, n_items, nchunks;
+  int ntiles, nblocks, n_items, nchunks, bchunk;
   int64_t wtotal;
   gnca_layout L;
   const float* zp_rowsum;   // row sums of x (zero-padded shift)
@@ -207,7 +208,7 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
-template <int C>
+template <int C, int CH>
 __global__ void __launch_bounds__(kBThreads) k_bwd_mlp(BwdArgs A, Packed P, int hid, const float* __restrict__ packed) {
   using K = BwdCfg<C>;
   constexpr int NB = K::NB, NBP = K::NBP, TPC = K::TPC, CQ = K::CQ, C3 = 3 * C;
@@ -261,10 +262,10 @@ __global__ void __launch_bounds__(kBThreads) k_bwd_mlp(BwdArgs A, Packed P, int 
     if (!sample_active(a, b)) continue;
     const float* xs_base = a.x_in + (size_t)b * C * HW;
     const unsigned char* am = A.actmask + (size_t)b * HW;
-    const int cell0 = chunk * kBChunk;
+    const int cell0 = chunk * CH;
     // ---- compaction of the chunk's active cells (same deterministic order as the forward) ----------
     {
-      constexpr int kPerWarp = kBChunk / (kBThreads / 32);
+      constexpr int kPerWarp = CH / (kBThreads / 32);
       uint32_t bal[kPerWarp / 32];
       int cnt = 0;
 #pragma unroll
@@ -690,7 +691,7 @@ static BwdWorkspace carve_bwd(void* base, const gnca_model& m, int B, int H, int
   w.wpart = reinterpret_cast<float*>(p + o);
   w.wpart_bytes = (size_t)kMaxBwdBlocks * L.total * 4;
   o = align_up_b(o + w.wpart_bytes, 256);
-  const int nchunks = (H * W + kBChunk - 1) / kBChunk;
+  const int nchunks = (H * W + kBChunkSmall - 1) / kBChunkSmall;   // sized for the small chunk
   w.attn = carve_attn_bwd(p + o, m, B, H, nchunks);
   w.gw_bytes = (size_t)B * nchunks * GNCA_MAX_K * 4;
   o += ((m.flags & GNCA_F_GRAPH) ? attn_bwd_scratch_bytes(m, B, H, nchunks) : 0);
@@ -714,9 +715,14 @@ static int launch_step_bwd(const gnca_model& m, const Packed& P, const float* pa
   GNCA_LAUNCH_CHECK();
   const size_t smem = BwdSmem<C>::bytes(m.hidden, graph);
   if (smem > 226 * 1024) return GNCA_ERR_UNSUPPORTED;
-  GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_mlp<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(PROF_BWD_MLP, st);
-  k_bwd_mlp<C><<<A.nblocks, kBThreads, smem, st>>>(A, P, m.hidden, packed);
+  if (A.bchunk == kBChunkSmall) {
+    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_mlp<C, kBChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bwd_mlp<C, kBChunkSmall><<<A.nblocks, kBThreads, smem, st>>>(A, P, m.hidden, packed);
+  } else {
+    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_mlp<C, kBChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bwd_mlp<C, kBChunk><<<A.nblocks, kBThreads, smem, st>>>(A, P, m.hidden, packed);
+  }
   prof_end(PROF_BWD_MLP, st);
   GNCA_LAUNCH_CHECK();
   if (A.gw_part) {
@@ -764,7 +770,8 @@ int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, cons
   A.actmask = w.actmask; A.postmask = w.postmask; A.gz = w.gz; A.gy = w.gy; A.gxs = w.gxs;
   A.tile_part = w.tile_part; A.sums = w.sums; A.wpart = w.wpart;
   A.ntiles = ((a.W + kBTileW - 1) / kBTileW) * ((a.H + kBTileH - 1) / kBTileH);
-  A.nchunks = (a.H * a.W + kBChunk - 1) / kBChunk;
+  A.bchunk = ((long long)a.B * ((a.H * a.W + kBChunk - 1) / kBChunk) < 2 * 148) ? kBChunkSmall : kBChunk;
+  A.nchunks = (a.H * a.W + A.bchunk - 1) / A.bchunk;
   A.n_items = a.B * A.nchunks;
   A.nblocks = A.n_items < kMaxBwdBlocks ? A.n_items : kMaxBwdBlocks;
   A.L = make_layout(m);

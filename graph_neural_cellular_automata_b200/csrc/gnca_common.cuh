@@ -134,7 +134,7 @@ struct StepArgs {
   float* u;                           // [B][C][H][W]
   float* stats;                       // [B][2]  (mean, rstd)
   double* partials;                   // [B][nchunks][2]
-  int nchunks;
+  int nchunks, chunk;                 // k_update work split: cells per block and blocks per sample
   Offsets off;                        // host-supplied offsets (single step)
 };
 

@@ -29,7 +29,8 @@ void prof_end(int id, cudaStream_t st) {
   cudaEventRecord(g_prof_ev[id].back().second, st);
 }
 
-constexpr int kChunk = 1024;    // cells per k_update block
+constexpr int kChunk = 1024;    // cells per k_update block (large problems)
+constexpr int kChunkSmall = 256; // ... when the grid would otherwise not fill the 148 SMs
 constexpr int kThreads = 256;
 constexpr int kTileW = 32, kTileH = 8;
 
@@ -170,7 +171,7 @@ struct UpdateSmem {
   }
 };
 
-template <int C>
+template <int C, int CH>
 __global__ void __launch_bounds__(kThreads) k_update(StepArgs a, Packed P, int hid, const float* __restrict__ packed) {
   constexpr int PC = CellsPerThread<C>::value;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -200,8 +201,8 @@ __global__ void __launch_bounds__(kThreads) k_update(StepArgs a, Packed P, int h
   const float* xs_base = a.x_in + (size_t)b * C * HW;
   const float* alpha = xs_base + 3 * HW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kPerWarp = kChunk / (kThreads / 32);  // 128 cells per warp
-  const int cell0 = chunk * kChunk;
+  constexpr int kPerWarp = CH / (kThreads / 32);      // cells per warp
+  const int cell0 = chunk * CH;
   uint32_t bal[kPerWarp / 32];
   int cnt = 0;
 #pragma unroll
@@ -462,7 +463,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 FwdWorkspace carve_fwd_workspace(void* base, const gnca_model& m, int B, int H, int W) {
   FwdWorkspace ws;
-  const int nchunks = (H * W + kChunk - 1) / kChunk;
+  const int nchunks = (H * W + kChunkSmall - 1) / kChunkSmall;   // sized for the small chunk
   size_t o = 0;
   char* p = reinterpret_cast<char*>(base);
   ws.partials = reinterpret_cast<double*>(p + o); o = align_up(o + (size_t)B * nchunks * 2 * sizeof(double), 256);
@@ -478,7 +479,9 @@ void fill_step_args(StepArgs& a, const gnca_model& m, int B, int H, int W) {
   a.B = B; a.H = H; a.W = W;
   a.flags = m.flags;
   a.update_gain = m.update_gain; a.alpha_thr = m.alpha_thr; a.graph_alpha_thr = m.graph_alpha_thr; a.gn_eps = m.gn_eps;
-  a.nchunks = (H * W + kChunk - 1) / kChunk;
+  // small chunks when 1024-cell chunks would leave SMs idle (launch-latency-bound small grids)
+  a.chunk = ((long long)B * ((H * W + kChunk - 1) / kChunk) < 2 * 148) ? kChunkSmall : kChunk;
+  a.nchunks = (H * W + a.chunk - 1) / a.chunk;
 }
 
 template <int C>
@@ -493,10 +496,15 @@ int launch_step_fwd(const gnca_model& m, const Packed& P, const float* packed, S
     if (rc) return rc;
   }
   const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
-  GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 g1(a.nchunks, a.B);
   prof_begin(PROF_UPDATE, st);
-  k_update<C><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
+  if (a.chunk == kChunkSmall) {
+    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_update<C, kChunkSmall><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
+  } else {
+    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_update<C, kChunk><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
+  }
   prof_end(PROF_UPDATE, st);
   GNCA_LAUNCH_CHECK();
   const int tiles = ((a.W + kTileW - 1) / kTileW) * ((a.H + kTileH - 1) / kTileH);
@@ -581,9 +589,14 @@ int launch_step_recompute(const gnca_model& m, const Packed& P, const float* pac
     if (rc) return rc;
   }
   const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
-  GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 g1(a.nchunks, a.B);
-  k_update<C><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
+  if (a.chunk == kChunkSmall) {
+    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_update<C, kChunkSmall><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
+  } else {
+    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_update<C, kChunk><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
+  }
   GNCA_LAUNCH_CHECK();
   k_finalize_stats<<<(a.B + 127) / 128, 128, 0, st>>>(a, C);
   GNCA_LAUNCH_CHECK();

@@ -656,17 +656,43 @@ static int launch_resident(const gnca_model& m, const Packed& P, const float* pa
   const int halo = (graph && R.s.k > 0 ? radius : 0) + 1;
   const char* env_nc = getenv("GNCA_RESIDENT_NC");      // development override of the cluster size
   const bool debug = getenv("GNCA_DEBUG") != nullptr;
+  // Cluster size: the largest NC in {8,4,2,1} whose bands are at least `halo` rows, that fits shared memory and
+  // keeps ALL B clusters co-resident (B <= cudaOccupancyMaxActiveClusters); if the batch is too large for that,
+  // the smallest NC that fits (most clusters per wave) and the launch runs in waves.
   const int cands[4] = {8, 4, 2, 1};
-  for (int ci = 0; ci < 4; ++ci) {
-    const int NC = cands[ci];
-    if (env_nc && atoi(env_nc) != NC) continue;
-    if (H % NC != 0 || H / NC < halo || H / NC > 255) continue;
-    if ((long long)B * NC > sms && NC > 1 && !env_nc) continue;     // keep the whole batch co-resident when possible
-    const int own = H / NC;
-    int MB = 64;
-    size_t smem = resident_smem_bytes(C, m.hidden, graph, own, halo, W, MB, R.s.k, R.T);
-    if (smem > 226 * 1024) { MB = 32; smem = resident_smem_bytes(C, m.hidden, graph, own, halo, W, MB, R.s.k, R.T); }
-    if (smem > 226 * 1024) continue;
+  int pick = -1, pick_MB = 0, pick_nclusters = 0;
+  size_t pick_smem = 0;
+  for (int pass = 0; pass < 2 && pick < 0; ++pass) {
+    for (int ci = (pass == 0 ? 0 : 3); ci >= 0 && ci < 4; ci += (pass == 0 ? 1 : -1)) {
+      const int NC = cands[ci];
+      if (env_nc && atoi(env_nc) != NC) continue;
+      if (H % NC != 0 || H / NC < halo || H / NC > 255) continue;
+      const int own = H / NC;
+      int MB = 64;
+      size_t smem = resident_smem_bytes(C, m.hidden, graph, own, halo, W, MB, R.s.k, R.T);
+      if (smem > 226 * 1024) { MB = 32; smem = resident_smem_bytes(C, m.hidden, graph, own, halo, W, MB, R.s.k, R.T); }
+      if (smem > 226 * 1024) continue;
+      GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_resident_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(B * NC); q.blockDim = dim3(kRThreads); q.dynamicSmemBytes = smem; q.stream = st;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = NC; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, k_resident_fwd<C>, &q) != cudaSuccess || nclusters < 1) {
+        cudaGetLastError();
+        continue;
+      }
+      if (pass == 0 && B > nclusters && !env_nc) continue;      // would need a second wave: try a smaller cluster
+      pick = NC; pick_MB = MB; pick_smem = smem; pick_nclusters = nclusters;
+      break;
+    }
+  }
+  if (pick < 0) return GNCA_ERR_UNSUPPORTED;
+  {
+    const int NC = pick, own = H / NC, MB = pick_MB;
+    const size_t smem = pick_smem;
     GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_resident_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(B * NC);
@@ -677,11 +703,7 @@ static int launch_resident(const gnca_model& m, const Packed& P, const float* pa
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, k_resident_fwd<C>, &cfg) != cudaSuccess || nclusters < 1) {
-      cudaGetLastError();
-      continue;
-    }
+    const int nclusters = pick_nclusters;
     if (debug)
       fprintf(stderr, "[gnca] resident fwd: B=%d NC=%d own_rows=%d halo=%d MB=%d smem=%zu maxActiveClusters=%d\n", B, NC,
               own, halo, MB, smem, nclusters);
@@ -714,7 +736,6 @@ static int launch_resident(const gnca_model& m, const Packed& P, const float* pa
     }
     return 0;
   }
-  return GNCA_ERR_UNSUPPORTED;
 }
 
 // entry used by gnca_rollout_fwd (impl 2 / auto)

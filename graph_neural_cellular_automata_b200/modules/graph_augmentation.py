@@ -22,6 +22,38 @@ def build_offsets(radius: int) -> List[Tuple[int, int]]:
     return [(dy, dx) for dy in span for dx in span if max(abs(dy), abs(dx)) >= 2]
 
 
+_FAST_SAMPLE_CACHE = {}
+
+
+def _fast_sample_ok(n: int, k: int) -> bool:
+    """True iff replaying random.sample's pool algorithm with random._randbelow reproduces random.sample(range(n), k)
+    (checked once per (n, k) on a saved/restored RNG state)."""
+    key = (n, k)
+    if key not in _FAST_SAMPLE_CACHE:
+        ok = False
+        try:
+            state = random.getstate()
+            try:
+                ref = [random.sample(range(n), k) for _ in range(3)]
+                random.setstate(state)
+                rb = random._randbelow
+                mine = []
+                for _ in range(3):
+                    pool, res = list(range(n)), []
+                    for i in range(k):
+                        j = rb(n - i)
+                        res.append(pool[j])
+                        pool[j] = pool[n - i - 1]
+                    mine.append(res)
+                ok = mine == ref
+            finally:
+                random.setstate(state)
+        except Exception:
+            ok = False
+        _FAST_SAMPLE_CACHE[key] = ok
+    return _FAST_SAMPLE_CACHE[key]
+
+
 class GraphAugmentation(nn.Module):
     def __init__(self, n_channels: int, d_model: int = 16, attention_radius: int = 4, num_neighbors: int = 8,
                  gating_hidden: int = 32, *, alive_to_alive: bool = True, zero_padded_shift: bool = True,
@@ -50,6 +82,31 @@ class GraphAugmentation(nn.Module):
         """The per-forward draw of graph_augmentation.py:120-121 (Python global RNG, also at message_gain 0)."""
         k = min(self.num_neighbors, len(self.offsets))
         return random.sample(self.offsets, k) if k > 0 else []
+
+    def draw_offsets_array(self, T: int):
+        """T consecutive `draw_offsets()` results as one int8 array [T,k,2] -- the SAME python-RNG stream as T
+        forward calls, drawn without per-step tuple/list churn (the rollout's host-side schedule construction).
+        `random.sample` on a short sequence is a partial Fisher-Yates over a copy of the population driven by
+        `random._randbelow`; that loop is replayed here on indices.  A one-time self-check against
+        `random.sample` guards the private-API assumption and falls back to plain `random.sample` if it fails."""
+        import numpy as np
+        n, k = len(self.offsets), min(self.num_neighbors, len(self.offsets))
+        table = np.asarray(self.offsets, dtype=np.int8).reshape(n, 2)
+        if k == 0 or T == 0:
+            return np.zeros((T, 0, 2), np.int8)
+        if _fast_sample_ok(n, k):
+            rb = random._randbelow
+            idx = []
+            for _ in range(T):
+                pool = list(range(n))
+                for i in range(k):
+                    j = rb(n - i)
+                    idx.append(pool[j])
+                    pool[j] = pool[n - i - 1]
+        else:
+            pos = {o: i for i, o in enumerate(self.offsets)}
+            idx = [pos[o] for _ in range(T) for o in random.sample(self.offsets, k)]
+        return table[np.asarray(idx, dtype=np.intp)].reshape(T, k, 2)
 
     def forward(self, x: torch.Tensor, return_attention_map: bool = False):
         from .. import graph_ops

@@ -47,6 +47,31 @@ class Schedule:
                             p(self.damage), self.damage_step, self.max_offset)
 
 
+class _PinnedRing:
+    """A few reusable pinned staging buffers (pinning memory per call costs ~100 us); a buffer is reused only after
+    the event recorded behind its last H2D copy has completed."""
+
+    def __init__(self, slots: int = 8):
+        self.slots, self.buf, self.ev, self.i = slots, [None] * slots, [None] * slots, 0
+
+    def get(self, nbytes: int):
+        i = self.i
+        self.i = (i + 1) % self.slots
+        if self.ev[i] is not None:
+            self.ev[i].synchronize()
+        if self.buf[i] is None or self.buf[i].numel() < nbytes:
+            self.buf[i] = torch.empty(max(nbytes, 1 << 14), dtype=torch.uint8).pin_memory()
+        return i, self.buf[i]
+
+    def mark(self, i: int):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.ev[i] = ev
+
+
+_RING = _PinnedRing()
+
+
 def _upload(arrs: Sequence[np.ndarray], device) -> List[torch.Tensor]:
     """One pinned staging buffer, one async H2D copy, typed device views."""
     sizes = [a.nbytes for a in arrs]
@@ -54,11 +79,21 @@ def _upload(arrs: Sequence[np.ndarray], device) -> List[torch.Tensor]:
     for s in sizes:
         offs.append(o)
         o += (s + 15) // 16 * 16
-    host = torch.empty(max(o, 16), dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else torch.empty(max(o, 16), dtype=torch.uint8)
+    total = max(o, 16)
+    on_cuda = torch.device(device).type == "cuda"
+    if on_cuda:
+        slot, host = _RING.get(total)
+    else:
+        host = torch.empty(total, dtype=torch.uint8)
     hv = host.numpy()
     for a, off in zip(arrs, offs):
-        hv[off:off + a.nbytes] = np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8)
-    dev = host.to(device, non_blocking=True)
+        hv[off:off + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    if on_cuda:
+        dev = torch.empty(total, dtype=torch.uint8, device=device)
+        dev.copy_(host[:total], non_blocking=True)
+        _RING.mark(slot)
+    else:
+        dev = host[:total].clone()
     out = []
     for a, off in zip(arrs, offs):
         t = dev[off:off + a.nbytes].view(torch.from_numpy(np.empty(0, a.dtype)).dtype).view(a.shape)
@@ -87,9 +122,14 @@ def make_schedule(model, B: int, H: int, W: int, T: int, *, fire_rate: Union[flo
     assert fr.shape == (T,)
     if is_graph:
         if offsets is None:
-            offsets = [model.graph.draw_offsets() for _ in range(T)]
-        k = len(offsets[0]) if T > 0 else 0
-        off = np.asarray(offsets, dtype=np.int8).reshape(T, k, 2) if k > 0 else np.zeros((T, 0, 2), np.int8)
+            off = model.graph.draw_offsets_array(T)          # same python-RNG stream as T forward calls
+        elif isinstance(offsets, np.ndarray):
+            off = offsets.astype(np.int8, copy=False).reshape(T, -1, 2)
+        else:
+            k_ = len(offsets[0]) if T > 0 else 0
+            flat = [v for st in offsets for o in st for v in o]
+            off = np.asarray(flat, dtype=np.int8).reshape(T, k_, 2) if k_ > 0 else np.zeros((T, 0, 2), np.int8)
+        k = off.shape[1]
         if message_gains is None:
             g = float(model.message_gain)
             message_gains = [g if (message_every <= 1 or t % message_every == 0) else 0.0 for t in range(T)]
