@@ -52,6 +52,6 @@ int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, cons
 // resident kernel (zero-padded graph shift, sample too large for the cluster's shared memory)
 int run_resident_fwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,
                      const gnca_schedule& sched, const float* x0, float* xT, float* hist, float* stats_hist,
-                     float* ping, float* pong, float* alpha_tmp, cudaStream_t st);
+                     float* u_hist, float* ping, float* pong, float* alpha_tmp, cudaStream_t st);
 
 }  // namespace gnca

@@ -38,6 +38,7 @@ struct ResidentArgs {
   float* xT;
   float* hist;                // [T+1][B][C][HW] or null
   float* stats_hist;          // [T][B][2] or null
+  float* u_hist;              // [T][B][C][HW] or null: masked pre-norm update of the active cells (for the backward)
   const float* damage;        // [B][C][HW] or null
   int damage_step;
   unsigned long long* dbg;    // optional phase-cycle counters (GNCA_PHASE_TIMING=<cta index>), else null
@@ -468,6 +469,8 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
                     const int c = 4 * cq + cc;
                     const float v = o2[m][cc] + MSGt[c * MBP + cl];
                     Ut[(size_t)c * nown + base + cl] = v;
+                    if (R.u_hist)
+                      R.u_hist[(((size_t)t * a.B + b) * C + c) * HW + r0 * W + s_actlist[base + cl]] = v;
                     ps1 += v;
                     ps2 = fmaf(v, v, ps2);
                   }
@@ -741,7 +744,7 @@ static int launch_resident(const gnca_model& m, const Packed& P, const float* pa
 // entry used by gnca_rollout_fwd (impl 2 / auto)
 int run_resident_fwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,
                      const gnca_schedule& sched, const float* x0, float* xT, float* hist, float* stats_hist,
-                     float* ping, float* pong, float* alpha_tmp, cudaStream_t st) {
+                     float* u_hist, float* ping, float* pong, float* alpha_tmp, cudaStream_t st) {
   (void)ping; (void)pong; (void)alpha_tmp;
   const bool graph = (m.flags & GNCA_F_GRAPH) != 0;
   if (graph && !(m.flags & GNCA_F_TORUS) && sched.k > 0) return GNCA_ERR_UNSUPPORTED;   // zero-pad: streaming path
@@ -757,7 +760,7 @@ int run_resident_fwd(const gnca_model& m, const Packed& P, const float* packed, 
   R.s.philox_offset = sched.philox_offset;
   R.fire_u_base = sched.fire_u;
   R.T = sched.T;
-  R.x0 = x0; R.xT = xT; R.hist = hist; R.stats_hist = stats_hist;
+  R.x0 = x0; R.xT = xT; R.hist = hist; R.stats_hist = stats_hist; R.u_hist = u_hist;
   R.damage = sched.damage; R.damage_step = sched.damage_step;
   const int radius = sched.max_offset;       // largest |dy| / |dx| in the schedule: sets the halo depth
   switch (m.C) {

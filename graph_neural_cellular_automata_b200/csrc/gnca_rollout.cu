@@ -71,7 +71,8 @@ size_t gnca_rollout_workspace_bytes(const gnca_model* m, int B, int H, int W, in
 }
 
 int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const gnca_schedule* sched,
-                     const float* x0_dev, float* xT_dev, float* x_hist_dev, float* stats_hist_dev, void* workspace_dev,
+                     const float* x0_dev, float* xT_dev, float* x_hist_dev, float* stats_hist_dev, float* u_hist_dev,
+                     void* workspace_dev,
                      size_t workspace_bytes, int impl, void* stream) {
   if (!m || !packed_dev || !sched || !x0_dev || !xT_dev || !workspace_dev) return GNCA_ERR_ARG;
   if (B <= 0 || H <= 0 || W <= 0 || sched->T < 0) return GNCA_ERR_ARG;
@@ -91,7 +92,7 @@ int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H,
     // auto: small samples (the launch-latency-bound regime) go to the cluster-resident kernel
     const bool want = impl == 2 || (size_t)H * W <= 16384;
     if (want) {
-      int rc = run_resident_fwd(*m, P, packed_dev, B, H, W, *sched, x0_dev, xT_dev, x_hist_dev, stats_hist_dev, r.ping,
+      int rc = run_resident_fwd(*m, P, packed_dev, B, H, W, *sched, x0_dev, xT_dev, x_hist_dev, stats_hist_dev, u_hist_dev, r.ping,
                                 r.pong, r.alpha_tmp, st);
       if (rc != GNCA_ERR_UNSUPPORTED || impl == 2) return rc;
     }
@@ -115,7 +116,7 @@ int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H,
     if (!graph) a.k = 0;
     a.x_in = x_at(t);
     a.x_out = x_at(t + 1);
-    a.u = r.u;
+    a.u = u_hist_dev ? u_hist_dev + (size_t)t * N : r.u;
     a.stats = stats_hist_dev ? stats_hist_dev + (size_t)t * B * 2 : r.stats;
     int rc = dispatch_step_fwd(*m, P, packed_dev, a, fws, nullptr, st);
     if (rc) return rc;
@@ -126,14 +127,15 @@ int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H,
 }
 
 int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const gnca_schedule* sched,
-                     const float* x_hist_dev, const float* stats_hist_dev, const float* gT_dev, float* g0_dev,
+                     const float* x_hist_dev, const float* stats_hist_dev, const float* u_hist_dev,
+                     const float* gT_dev, float* g0_dev,
                      float* gparams_dev, void* workspace_dev, size_t workspace_bytes, int impl, void* stream) {
   if (!m || !packed_dev || !sched || !x_hist_dev || !gT_dev || !g0_dev || !gparams_dev || !workspace_dev)
     return GNCA_ERR_ARG;
   if (B <= 0 || H <= 0 || W <= 0 || sched->T < 0) return GNCA_ERR_ARG;
   if (!model_supported(*m)) return GNCA_ERR_UNSUPPORTED;
   (void)impl;             // the backward currently always takes the streaming kernels (x_hist layout is shared)
-  (void)stats_hist_dev;   // statistics are recomputed together with u
+  const bool saved = u_hist_dev != nullptr && stats_hist_dev != nullptr;   // else u and the statistics are recomputed
   const bool graph = (m->flags & GNCA_F_GRAPH) != 0;
   cudaStream_t st = (cudaStream_t)stream;
   RolloutWorkspace r = carve_rollout(workspace_dev, *m, B, H, W);
@@ -155,12 +157,19 @@ int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H,
     if (!graph) a.k = 0;
     a.x_in = x_hist_dev + (size_t)t * N;
     a.x_out = nullptr;
-    a.u = r.u;
-    a.stats = r.stats;
-    int rc = dispatch_step_recompute(*m, P, packed_dev, a, fws, st);
-    if (rc) return rc;
+    const float* stats_t = r.stats;
+    int rc = 0;
+    if (saved) {
+      a.u = const_cast<float*>(u_hist_dev) + (size_t)t * N;
+      stats_t = stats_hist_dev + (size_t)t * B * 2;
+    } else {
+      a.u = r.u;
+      a.stats = r.stats;
+      rc = dispatch_step_recompute(*m, P, packed_dev, a, fws, st);
+      if (rc) return rc;
+    }
     float* gnext = (t == 0) ? g0_dev : (((T - 1 - t) & 1) ? r.g_b : r.g_a);
-    rc = run_step_bwd(*m, P, packed_dev, a, r.stats, gcur, gnext, gparams_dev, fws, bws, t == T - 1, t == 0, st);
+    rc = run_step_bwd(*m, P, packed_dev, a, stats_t, gcur, gnext, gparams_dev, fws, bws, t == T - 1, t == 0, st);
     if (rc) return rc;
     if (sched->damage && t == sched->damage_step) {
       k_mul_inplace<<<(int)((N + 1023) / 1024 < 2368 ? (N + 1023) / 1024 : 2368), 256, 0, st>>>(N, gnext, sched->damage);

@@ -165,8 +165,24 @@ def make_schedule(model, B: int, H: int, W: int, T: int, *, fire_rate: Union[flo
     return sched
 
 
-def rollout_fwd_raw(desc, packed, x0: torch.Tensor, sched: Schedule, *, history: bool, impl: int = 0):
-    """gnca_rollout_fwd without autograd: returns (x_T, x_hist or None)."""
+class History:
+    """What the forward keeps for BPTT: x_t for every step, and (optionally) the masked pre-norm update of the
+    active cells + the GroupNorm statistics so that the backward does not re-run the forward MLP."""
+
+    def __init__(self, x, u=None, stats=None):
+        self.x, self.u, self.stats = x, u, stats
+
+    @property
+    def shape(self):
+        return self.x.shape
+
+    def __getitem__(self, i):
+        return self.x[i]
+
+
+def rollout_fwd_raw(desc, packed, x0: torch.Tensor, sched: Schedule, *, history: bool, impl: int = 0,
+                    keep_u: bool = True):
+    """gnca_rollout_fwd without autograd: returns (x_T, History or None)."""
     x0 = GF._require_cuda_f32(x0, "x0")
     B, Cc, H, W = x0.shape
     if Cc != desc.C:
@@ -174,19 +190,26 @@ def rollout_fwd_raw(desc, packed, x0: torch.Tensor, sched: Schedule, *, history:
     lib = _lib.load()
     T = sched.T
     xT = torch.empty_like(x0)
-    hist = torch.empty(T + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device) if history else None
+    hist = uh = sh = None
+    if history:
+        hist = torch.empty(T + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device)
+        if keep_u and T > 0:
+            uh = torch.empty(T, B, Cc, H, W, dtype=torch.float32, device=x0.device)
+            sh = torch.empty(T, B, 2, dtype=torch.float32, device=x0.device)
     nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, T)
     ws = GF._WS.get(x0.device, nbytes)
     cs = sched.c_struct()
     _lib.check(lib.gnca_rollout_fwd(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(x0), GF._ptr(xT),
-                                    GF._ptr(hist), C.c_void_p(0), GF._ptr(ws), ws.numel(), int(impl), GF._stream()),
-               "gnca_rollout_fwd")
-    return xT, hist
+                                    GF._ptr(hist), GF._ptr(sh), GF._ptr(uh), GF._ptr(ws), ws.numel(), int(impl),
+                                    GF._stream()), "gnca_rollout_fwd")
+    return xT, (History(hist, uh, sh) if history else None)
 
 
-def rollout_bwd_raw(desc, packed, hist: torch.Tensor, sched: Schedule, gT: torch.Tensor, *, gflat=None, impl: int = 0):
+def rollout_bwd_raw(desc, packed, hist, sched: Schedule, gT: torch.Tensor, *, gflat=None, impl: int = 0):
     """gnca_rollout_bwd without autograd: returns (dL/dx_0, flat parameter gradient in canonical layout).
     `gflat` (optional) is accumulated into."""
+    if not isinstance(hist, History):
+        hist = History(hist)
     _, B, Cc, H, W = hist.shape
     gT = GF._require_cuda_f32(gT, "grad_output")
     lib = _lib.load()
@@ -197,9 +220,9 @@ def rollout_bwd_raw(desc, packed, hist: torch.Tensor, sched: Schedule, gT: torch
     nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, sched.T)
     ws = GF._WS.get(gT.device, nbytes)
     cs = sched.c_struct()
-    _lib.check(lib.gnca_rollout_bwd(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(hist), C.c_void_p(0),
-                                    GF._ptr(gT), GF._ptr(g0), GF._ptr(gflat), GF._ptr(ws), ws.numel(), int(impl),
-                                    GF._stream()), "gnca_rollout_bwd")
+    _lib.check(lib.gnca_rollout_bwd(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(hist.x),
+                                    GF._ptr(hist.stats), GF._ptr(hist.u), GF._ptr(gT), GF._ptr(g0), GF._ptr(gflat),
+                                    GF._ptr(ws), ws.numel(), int(impl), GF._stream()), "gnca_rollout_bwd")
     return g0, gflat
 
 
@@ -212,8 +235,8 @@ class _RolloutFn(torch.autograd.Function):
         ctx.param_shapes = [p.shape for p in params]
         ctx.hist = hist
         if cfg["history"]:
-            ctx.mark_non_differentiable(hist)
-            return xT, hist
+            ctx.mark_non_differentiable(hist.x)
+            return xT, hist.x
         return xT
 
     @staticmethod

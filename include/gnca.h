@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GNCA_VERSION 101
+#define GNCA_VERSION 102
 
 #define GNCA_ERR_ARG (-1)         /* null pointer / bad size */
 #define GNCA_ERR_UNSUPPORTED (-2) /* shape or flag combination without a kernel */
@@ -152,17 +152,20 @@ size_t gnca_rollout_workspace_bytes(const gnca_model* m, int B, int H, int W, in
 /*
  * T steps in one call.  x_hist_dev: NULL for inference, else [T+1][B][C][H][W] receives x_0..x_T
  * (what the backward recomputes from; x_T is also written to xT_dev).  stats_hist_dev: [T][B][2] or NULL.
+ * u_hist_dev: optional [T][B][C][H][W]; when given (together with stats_hist_dev) the masked pre-norm update of
+ * the ACTIVE cells of every step is kept, and gnca_rollout_bwd skips recomputing the forward MLP.
  * `impl`: 0 = auto, 1 = streaming per-step kernels (any shape), 2 = cluster-resident kernel
  * (state lives in shared memory across all T steps; needs the sample to fit, torus or classic).
  */
 int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W,
                      const gnca_schedule* sched, const float* x0_dev, float* xT_dev,
-                     float* x_hist_dev, float* stats_hist_dev,
+                     float* x_hist_dev, float* stats_hist_dev, float* u_hist_dev,
                      void* workspace_dev, size_t workspace_bytes, int impl, void* stream);
 
 /* BPTT: given gT = dL/dx_T and the x_hist of the forward, produce g0 = dL/dx_0 and ACCUMULATE gparams. */
 int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H, int W,
                      const gnca_schedule* sched, const float* x_hist_dev, const float* stats_hist_dev,
+                     const float* u_hist_dev,
                      const float* gT_dev, float* g0_dev, float* gparams_dev,
                      void* workspace_dev, size_t workspace_bytes, int impl, void* stream);
 
