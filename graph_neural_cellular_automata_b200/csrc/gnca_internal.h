@@ -54,4 +54,10 @@ int run_resident_fwd(const gnca_model& m, const Packed& P, const float* packed, 
                      const gnca_schedule& sched, const float* x0, float* xT, float* hist, float* stats_hist,
                      float* u_hist, float* ping, float* pong, float* alpha_tmp, cudaStream_t st);
 
+// replicated-state cluster rollout (gnca_rep.cu): every CTA of a sample's cluster holds the whole sample; first
+// choice of the resident path.  scratch: >= B*C*H*W floats of device memory (overflow of the in-smem u buffer).
+int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,
+                const gnca_schedule& sched, const float* x0, float* xT, float* hist, float* stats_hist,
+                float* u_hist, float* scratch, cudaStream_t st);
+
 }  // namespace gnca

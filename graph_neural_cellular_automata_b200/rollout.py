@@ -251,7 +251,7 @@ class _RolloutFn(torch.autograd.Function):
         return (g0, None, *grads)
 
 
-IMPL = {"auto": 0, "streaming": 1, "resident": 2}
+IMPL = {"auto": 0, "streaming": 1, "resident": 2, "banded": 3}
 
 
 def rollout(model, x0: torch.Tensor, schedule: Schedule, *, return_history: bool = False, impl: str = "auto"):

@@ -154,8 +154,9 @@ size_t gnca_rollout_workspace_bytes(const gnca_model* m, int B, int H, int W, in
  * (what the backward recomputes from; x_T is also written to xT_dev).  stats_hist_dev: [T][B][2] or NULL.
  * u_hist_dev: optional [T][B][C][H][W]; when given (together with stats_hist_dev) the masked pre-norm update of
  * the ACTIVE cells of every step is kept, and gnca_rollout_bwd skips recomputing the forward MLP.
- * `impl`: 0 = auto, 1 = streaming per-step kernels (any shape), 2 = cluster-resident kernel
- * (state lives in shared memory across all T steps; needs the sample to fit, torus or classic).
+ * `impl`: 0 = auto, 1 = streaming per-step kernels (any shape), 2 = cluster-resident kernels
+ * (state lives in shared memory across all T steps; needs the sample to fit, torus or classic: the
+ * replicated-state kernel when the whole sample fits one CTA, else the banded one), 3 = banded kernel only.
  */
 int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W,
                      const gnca_schedule* sched, const float* x0_dev, float* xT_dev,

@@ -17,7 +17,7 @@ if torch.cuda.is_available():
     from graph_neural_cellular_automata_b200.rollout import make_schedule, rollout
     from test_gpu_step import graph_model, classic_model, T32, tup, DEV
 
-IMPLS = ["streaming", "resident"]
+IMPLS = ["streaming", "resident", "banded"]
 
 
 def _supported(impl, fn):
@@ -25,7 +25,7 @@ def _supported(impl, fn):
     try:
         return fn()
     except GncaError as e:
-        if impl == "resident" and "unsupported" in str(e):
+        if impl in ("resident", "banded") and "unsupported" in str(e):
             pytest.skip("resident kernel not available for this configuration")
         raise
 
