@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--rollout-impl", default="auto", choices=["auto", "streaming", "resident"])
+    ap.add_argument("--rollout-impl", default="auto", choices=["auto", "streaming", "resident", "banded"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--T", type=int, default=0, help="development: override the number of CA steps per rollout")
     ap.add_argument("--B", type=int, default=0, help="development: override the per-GPU batch")
@@ -253,12 +253,12 @@ def main():
         from graph_neural_cellular_automata_b200.training.optim import FusedNormalizedAdam
         from graph_neural_cellular_automata_b200.rollout import rollout_fwd_raw, rollout_bwd_raw
         opt = FusedNormalizedAdam(model, lr=2e-4, weight_decay=1e-5, normalize=True)
-        IMPLN = {"auto": 0, "streaming": 1, "resident": 2}[args.rollout_impl]
+        IMPLN = {"auto": 0, "streaming": 1, "resident": 2, "banded": 3}[args.rollout_impl]
 
     def one_rollout(x0, sched):
         if cfg["train"]:     # fwd (history) + premult loss + BPTT + grad normalise + Adam: one training iteration's hot path
             desc, packed = model.model_desc(), model.packed_weights()
-            xT, hist = rollout_fwd_raw(desc, packed, x0, sched, history=True, impl=IMPLN)
+            xT, hist = rollout_fwd_raw(desc, packed, x0, sched, history=True, impl=IMPLN, keep_x=False)
             per, gxT = premult_loss(xT, target, 1.0 / (B * world))
             _, gflat = rollout_bwd_raw(desc, packed, hist, sched, gxT, impl=IMPLN)
             if world > 1:

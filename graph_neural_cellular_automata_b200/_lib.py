@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_PKG, "lib", "libgnca.so")
 
 GNCA_F_GRAPH, GNCA_F_TORUS, GNCA_F_HIDDEN_ONLY, GNCA_F_ALIVE_TO_ALIVE, GNCA_F_GROUPNORM = 1, 2, 4, 8, 16
 GNCA_MAX_K = 64
-GNCA_VERSION = 102
+GNCA_ERR_ARG, GNCA_ERR_UNSUPPORTED = -1, -2
+GNCA_VERSION = 103
 
 
 class GncaModel(C.Structure):
@@ -66,6 +67,13 @@ EXPORTS = {
     "gnca_rollout_bwd": (C.c_int, [C.POINTER(GncaModel), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(GncaSchedule), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "gnca_bptt_bytes": (C.c_size_t, [C.POINTER(GncaModel), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gnca_rollout_fwd_bptt": (C.c_int, [C.POINTER(GncaModel), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(GncaSchedule), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnca_rollout_bwd_bptt": (C.c_int, [C.POINTER(GncaModel), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(GncaSchedule), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnca_loss_premult_rgba": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 4 + [C.c_float, C.c_void_p]),
     "gnca_normalize_adam": (C.c_int, [C.c_void_p] * 4 + [C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),

@@ -19,6 +19,7 @@
 #include <type_traits>
 #include "gnca_common.cuh"
 #include "gnca_internal.h"
+#include "gnca_rep.h"
 
 namespace cg = cooperative_groups;
 
@@ -40,6 +41,8 @@ struct RepArgs {
   float* hist;                // [T+1][B][C][HW] or null
   float* stats_hist;          // [T][B][2] or null
   float* u_hist;              // [T][B][C][HW] or null (dense layout, active cells only)
+  float* rec;                 // [T][B][HW][kRecStride] or null: per-active-cell records for the resident backward
+  uint32_t* masks;            // [T][B][3][kMaskWords] or null: sender-alive, active, post-alive bitmaps of every step
   float* u_over;              // [B*NC][over_cap][C] overflow of the in-smem u buffer
   int over_cap;
   const float* damage;        // [B][C][HW] or null
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     if (lane == 0) s_wtot[warp] = c0 + c1 + c2 + c3;
   };
   // balanced list of MY share of the active cells (slot order = cell order, deterministic)
-  int n_my = 0, nact = 0;
+  int n_my = 0, nact = 0, lo_my = 0;
   auto list_pass = [&]() {
     int base = 0, tot = 0;
 #pragma unroll
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     nact = tot;
     const int lo = (tot * rank) >> lnc, hi = (tot * (rank + 1)) >> lnc;
     n_my = hi - lo;
+    lo_my = lo;
     if (r_actnib) {
       int slot = base + r_pre + __popc(r_actword & ((1u << qsh) - 1u));
 #pragma unroll
@@ -391,6 +395,11 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     const bool msg_on = graph && gain_m != 0.f && k > 0;
     REP_MARK(0);
     if (R.dbg && tid == 0) s_dbg[8] += n_my;
+    if (R.masks && rank == 0 && tid < NW) {
+      uint32_t* mk = R.masks + ((size_t)t * a.B + b) * 3 * kMaskWords;
+      mk[tid] = s_bAliveS[tid];
+      mk[kMaskWords + tid] = s_bAct[tid];
+    }
 
     // ---- S2: warp-autonomous tiles of G cells; then the side jobs of the step (fire bits of step t+1, BPTT
     //      history of x_t) handed out in chunks by a shared counter, so the warps without a tile take them ----------
@@ -436,7 +445,8 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
           const float a10 = lf ? p[-st] : 0.f, a12 = rt ? p[st] : 0.f;
           const float a20 = (dn && lf) ? p[(W - 1) * st] : 0.f, a21 = dn ? p[W * st] : 0.f,
                       a22 = (dn && rt) ? p[(W + 1) * st] : 0.f;
-          myY[c * G + m] = p[0];
+          const float v_id = p[0];
+          myY[c * G + m] = v_id;
           myY[(C + c) * G + m] = (a00 - a02) + 2.f * (a10 - a12) + (a20 - a22);
           myY[(2 * C + c) * G + m] = (a00 + 2.f * a01 + a02) - (a20 + 2.f * a21 + a22);
           float xsv = 0.f, as = 0.f;
@@ -459,6 +469,12 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
             as = s_astab[nv];
           }
           xs[r] = xsv; asv[r] = as;
+          if (R.rec && slot0 + m < n_my) {          // forward half of the record (gnca_rep.h): y | u | xs | tanh(agg) | as
+            float* rc = R.rec + (((size_t)t * a.B + b) * HW + (size_t)(lo_my + slot0 + m)) * kRecStride;
+            rc[c] = v_id; rc[C + c] = myY[(C + c) * G + m]; rc[2 * C + c] = myY[(2 * C + c) * G + m];
+            rc[kRecXs + c] = xsv;
+            if (c == 0) rc[kRecAs] = as;
+          }
         }
         // 2c: message projection + channel policy (ncagraph.py:94-104,141): lane's row of Wm in registers
 #pragma unroll
@@ -468,7 +484,10 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
             float agg = bm_c * asv[r];
 #pragma unroll
             for (int ci = 0; ci < C; ++ci) agg = fmaf(wm[ci], __shfl_sync(0xffffffffu, xs[r], (lane & 16) | ci), agg);
-            if (c >= c_lo) mval = tanhf(agg) * gain_m;
+            const float th = tanhf(agg);
+            if (c >= c_lo) mval = th * gain_m;
+            if (R.rec && slot0 + hwi + CPL * r < n_my)
+              R.rec[(((size_t)t * a.B + b) * HW + (size_t)(lo_my + slot0 + hwi + CPL * r)) * kRecStride + kRecTh + c] = th;
           }
           msg[r] = mval;
         }
@@ -546,6 +565,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
             const int slot = slot0 + m;
             if (slot < n_my) {
               const float u = pv[e] + msg[r];
+              if (R.rec) R.rec[(((size_t)t * a.B + b) * HW + (size_t)(lo_my + slot)) * kRecStride + kRecU + c] = u;
               float* dst = slot < R.ucap ? sU + slot * C + c : over + (size_t)(slot - R.ucap) * C + c;
               *dst = u;
               if (R.u_hist) {
@@ -742,6 +762,10 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
       at.x = (post & 1u) ? at.x : 0.f; at.y = (post & 2u) ? at.y : 0.f;
       at.z = (post & 4u) ? at.z : 0.f; at.w = (post & 8u) ? at.w : 0.f;
       reinterpret_cast<float4*>(sAg)[qs] = at;
+      if (R.masks) {
+        const uint32_t pw = pack_nibbles(post, lane);
+        if (rank == 0 && (lane & 7) == 0 && qword < NW) R.masks[(((size_t)t * a.B + b) * 3 + 2) * kMaskWords + qword] = pw;
+      }
       if (fast_alive) {
         pack_store(s_bAlive, post);
         act_count(post, cur ^ 1);
@@ -777,7 +801,7 @@ static size_t rep_smem_bytes(int C, int HW, int ucap, int listcap) {
 
 int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,
                 const gnca_schedule& sched, const float* x0, float* xT, float* hist, float* stats_hist,
-                float* u_hist, float* scratch /* >= B*C*H*W floats */, cudaStream_t st) {
+                float* u_hist, float* rec, uint32_t* masks, float* scratch /* >= B*C*H*W floats */, cudaStream_t st) {
   const bool graph = (m.flags & GNCA_F_GRAPH) != 0;
   if (m.C != 16 || m.hidden != 128) return GNCA_ERR_UNSUPPORTED;
   if (H > kMaxRows || W > kMaxRows || H < 1 || W < 4 || (W & 3)) return GNCA_ERR_UNSUPPORTED;   // quads of 4 cells per row
@@ -802,6 +826,7 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
   R.fire_u_base = sched.fire_u;
   R.T = sched.T;
   R.x0 = x0; R.xT = xT; R.hist = hist; R.stats_hist = stats_hist; R.u_hist = u_hist;
+  R.rec = rec; R.masks = masks;
   R.damage = sched.damage; R.damage_step = sched.damage_step;
   R.KP = k > 8 ? 16 : 8;
   R.HWp = 4 * (((HW >> 2) + 31) & ~31) + 16;      // planes padded to whole warps of quads + one scratch quad

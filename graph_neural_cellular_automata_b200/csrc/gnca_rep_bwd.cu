@@ -1,0 +1,842 @@
+// Cluster-resident BPTT for the replicated-state rollout (gnca_rep.cu) -- SURVEY Appendix A, restated for records.
+//
+// The forward kept, for every ACTIVE cell of every step, a record (gnca_rep.h): perception y, masked pre-norm update u,
+// gathered sender state xs, tanh of the message pre-activation, `as`; plus three bitmaps and (mean, rstd) per step.
+// Nothing else of the forward is needed: no x_t history, no gathers, no perception recompute.
+//
+//   k_rep_bwd   ONE launch walks t = T-1 .. 0.  A sample is owned by a cluster of NC CTAs.  The sequential part of BPTT
+//               is only the propagation of g = dL/dx_t; per step:
+//                 A0  inactive cells of my band: per-channel sums of the gated gradient (their tanh' is a per-channel
+//                     constant) -> their share of the GroupNorm-backward sums S1, S2, dgamma, dbeta
+//                 A   my share of the ACTIVE cells (balanced over the cluster like the forward): gz = g * eta * tanh'
+//                 --  S1, S2 partials -> every CTA of the cluster (DSMEM)                        [cluster barrier 1]
+//                 B   warp-autonomous tiles: gd = dL/du, hidden layer recomputed from y in registers, gh, gy = W1^T gh as
+//                     three 16-channel shuffle reduce-scatters, message backward; gd / gm go back into the record, gy and
+//                     g_xs of the cell into an L2-resident per-cell scratch                       [cluster barrier 2]
+//                 C   my band of cells: g_t = gated g_{t+1} + perception transpose (gather from active neighbours) +
+//                     message transpose (gather from active receivers at +offset)                  [cluster barrier 3]
+//               g lives in L2 (cell-major ping-pong, 100 KB per sample) because an active cell may be handled by any CTA
+//               of the cluster; my band of it is also kept in shared memory.
+//   k_rep_wgrad weight gradients have no sequential dependence: one fully parallel pass over ALL records of the rollout
+//               (batches of 64 cells through the small GEMMs as FFMA register tiles, accumulators in registers for the
+//               whole kernel, one partial per block, no atomics) -> k_rep_wreduce sums the partials in a fixed order.
+#include <cooperative_groups.h>
+#include <cstdio>
+#include <cstdlib>
+#include "gnca_common.cuh"
+#include "gnca_internal.h"
+#include "gnca_rep.h"
+
+namespace cg = cooperative_groups;
+
+namespace gnca {
+
+constexpr int kQT = 512;          // threads per CTA (k_rep_bwd)
+constexpr int kQW = kQT / 32;
+constexpr int kQW2S = 20;         // padded row stride of W2^T
+constexpr int kQG = 4;            // cells per tile
+
+struct RepBwdArgs {
+  StepArgs s;
+  int T, NC, ucap, over_cap;
+  float inv_n;
+  float* rec;
+  const uint32_t* masks;
+  const float* stats;         // [T][B][2]
+  const float* gT;            // [B][C][HW]
+  float* g0;                  // [B][C][HW]
+  float* Gbuf;                // [2][B][HW][C] cell-major ping-pong of g (L2)
+  float* RG;                  // [B][HW][64]   gy (48) | g_xs (16) of the active cells of the current step (L2)
+  float* over;                // [B*NC][over_cap][C] overflow of the in-smem gz buffer
+  float* affpart;             // [B*NC][2C] dgamma | dbeta partials
+  const float* damage;
+  int damage_step;
+};
+
+__device__ __forceinline__ void cl_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, const float* __restrict__ packed) {
+  static_assert(C == 16, "lane mapping: 2 cells x 16 channels per warp row");
+  constexpr int C3 = 3 * C, HID = 128, G = kQG, CPL = 32 / C, MPL = G / CPL;
+  cg::cluster_group cluster = cg::this_cluster();
+  const StepArgs& a = R.s;
+  const int NC = R.NC;
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / NC;
+  const int H = a.H, W = a.W, HW = H * W;
+  const int NQ = HW >> 2, NW = (HW + 31) >> 5;
+  const bool graph = (a.flags & GNCA_F_GRAPH) != 0;
+  const bool gn = (a.flags & GNCA_F_GROUPNORM) != 0;
+  const bool a2a = (a.flags & GNCA_F_ALIVE_TO_ALIVE) != 0;
+  const int c_lo = ((a.flags & GNCA_F_HIDDEN_ONLY) && C >= 4) ? 4 : 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hwi = lane / C, c = lane % C;
+  const int k = a.k;
+  const int lnc = NC == 8 ? 3 : NC == 4 ? 2 : NC == 2 ? 1 : 0;
+  const float eta = a.update_gain;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sW1T = reinterpret_cast<float*>(smem_raw);           // [3C][HID] permuted (lane l owns 4l..4l+3 <-> units l+32jj)
+  float* sb1 = sW1T + C3 * HID;
+  float* sW2P = sb1 + HID;                                    // [HID][kQW2S]
+  const int band_lo = (HW * rank) >> lnc, band_hi = (HW * (rank + 1)) >> lnc, nband = band_hi - band_lo;
+  const int bandcap = ((HW + NC - 1) / NC) + 1;
+  float* sG = sW2P + HID * kQW2S;                             // [bandcap][C] my band of g (cell-major)
+  float* sGZ = sG + (size_t)bandcap * C;                      // [ucap][C] gz of my active cells
+  float* sY = sGZ + (size_t)R.ucap * C;                       // [kQW][3C][G]
+  float* sGD = sY + kQW * C3 * G;                             // [kQW][C][G]
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(sGD + kQW * C * G);   // [bandcap] cell index of my active cells
+
+  __shared__ uint32_t s_bAS[kMaskWords], s_bAct[kMaskWords], s_bPost[kMaskWords];
+  __shared__ __align__(16) int s_wtot[kQW];
+  __shared__ float s_parts[8][2];
+  __shared__ float s_wred[kQW][2];
+  __shared__ float s_chs[kQW][2][C];       // per-warp per-channel sums (A0)
+  __shared__ float s_aff[4][C];            // sc, bi, k_c = eta(1 - tanh(bi)^2), inactive gz factor ...
+  __shared__ float s_sums[2];
+  __shared__ signed char s_off[2 * 16];
+  __shared__ float s_gain;
+
+#pragma unroll 1
+  for (int i = tid; i < C3 * HID; i += kQT) {
+    const int kk = i / HID, jp = i - kk * HID;
+    const int l = jp >> 2, jj = jp & 3;
+    sW1T[i] = packed[P.w1t + kk * HID + (l + 32 * jj)];
+  }
+  if (tid < HID) { const int l = tid >> 2, jj = tid & 3; sb1[tid] = packed[P.b1 + l + 32 * jj]; }
+#pragma unroll 1
+  for (int i = tid; i < HID * C; i += kQT) { const int j = i / C, cc = i - j * C; sW2P[j * kQW2S + cc] = packed[P.w2t + i]; }
+  float wmT[C];                                              // Wm[cc][c]: column of this lane's INPUT channel
+#pragma unroll
+  for (int cc = 0; cc < C; ++cc) wmT[cc] = graph ? packed[P.wm + cc * C + c] : 0.f;
+  const float gam_c = gn ? packed[P.gamma + c] : 1.f, bet_c = gn ? packed[P.beta + c] : 0.f;
+
+  const size_t sample_off = (size_t)b * C * HW;
+  float* Gs[2] = {R.Gbuf + ((size_t)0 * a.B + b) * HW * C, R.Gbuf + ((size_t)1 * a.B + b) * HW * C};
+  float* RGs = R.RG + (size_t)b * HW * 64;
+  float* over = R.over ? R.over + (size_t)blockIdx.x * R.over_cap * C : nullptr;
+
+  // g_T (NCHW) -> my band in smem + cell-major global copy
+  {
+    const int n8 = (nband + 7) & ~7;
+#pragma unroll 1
+    for (int i = tid; i < n8 * C; i += kQT) {
+      const int ci = i & 7, c4 = (i >> 3) & 3, rest = i >> 5;
+      const int cq = rest & 3, cgp = rest >> 2;
+      const int cl = cgp * 8 + ci, ch = cq * 4 + c4;
+      if (cl < nband) {
+        const float v = R.gT[sample_off + (size_t)ch * HW + band_lo + cl];
+        sG[cl * C + ch] = v;
+        Gs[0][(size_t)(band_lo + cl) * C + ch] = v;
+      }
+    }
+  }
+  __syncthreads();
+  cl_sync_all();
+
+  const int my_steps = a.steps ? min(a.steps[b], R.T) : R.T;
+  const int q = tid, qcell = 4 * tid;
+  const bool qv = q < NQ;
+  const int qy = qcell / W, qx0 = qcell - qy * W;
+  const int qsh = 4 * (lane & 7), qword = min(q >> 3, kMaskWords - 1);
+  float* myY = sY + warp * (C3 * G);
+  float* myGD = sGD + warp * (C * G);
+  float dgam = 0.f, dbet = 0.f;              // this lane's channel c, summed over its cells / steps
+  int cur = 0;
+
+  for (int t = R.T - 1; t >= 0; --t) {
+    const bool dmg = R.damage && t == R.damage_step;
+    if (t >= my_steps) {                     // frozen: g passes through (the damage mask still multiplies x)
+      if (dmg) {
+        const float* D = R.damage + sample_off;
+#pragma unroll 1
+        for (int i = tid; i < nband * C; i += kQT) {
+          const int cl = i / C, ch = i - cl * C;
+          const float v = sG[i] * D[(size_t)ch * HW + band_lo + cl];
+          sG[i] = v;
+          Gs[cur][(size_t)(band_lo + cl) * C + ch] = v;
+        }
+        __syncthreads();
+        cl_sync_all();
+      }
+      continue;
+    }
+    // ---- masks, schedule, statistics of step t ----------------------------------------------------------------
+    if (tid < NW) {
+      const uint32_t* mk = R.masks + ((size_t)t * a.B + b) * 3 * kMaskWords;
+      s_bAS[tid] = mk[tid]; s_bAct[tid] = mk[kMaskWords + tid]; s_bPost[tid] = mk[2 * kMaskWords + tid];
+    }
+    if (tid >= 64 && tid < 64 + 2 * k) s_off[tid - 64] = a.offsets_dev[(size_t)t * k * 2 + (tid - 64)];
+    if (tid == 96) s_gain = graph ? a.message_gain_dev[t] : 0.f;
+    if (tid >= 128 && tid < 128 + C) {
+      const int ch = tid - 128;
+      float sc = 1.f, bi = 0.f;
+      if (gn) {
+        const float mu = R.stats[((size_t)t * a.B + b) * 2], rstd = R.stats[((size_t)t * a.B + b) * 2 + 1];
+        sc = rstd * packed[P.gamma + ch];
+        bi = packed[P.beta + ch] - mu * sc;
+      }
+      const float th = tanhf(bi);
+      s_aff[0][ch] = sc; s_aff[1][ch] = bi; s_aff[2][ch] = eta * (1.f - th * th);
+    }
+    __syncthreads();
+    const float gain_m = s_gain;
+    const bool msg_on = graph && gain_m != 0.f && k > 0;
+    const float mu = gn ? R.stats[((size_t)t * a.B + b) * 2] : 0.f, rstd = gn ? R.stats[((size_t)t * a.B + b) * 2 + 1] : 1.f;
+    const float uh0 = -mu * rstd;            // normalised update of an inactive cell
+    // ---- balanced list of my share of the active cells (same order as the forward: cell order) -------------------
+    int n_my, lo_my, nact;
+    {
+      const uint32_t wd = s_bAct[qword];
+      const uint32_t nib = qv ? (wd >> qsh) & 15u : 0u;
+      const int cnt = ((lane & 7) == 0 && qv) ? __popc(wd) : 0;
+      const int c0 = __shfl_sync(0xffffffffu, cnt, 0), c1 = __shfl_sync(0xffffffffu, cnt, 8),
+                c2 = __shfl_sync(0xffffffffu, cnt, 16), c3 = __shfl_sync(0xffffffffu, cnt, 24);
+      const int g = lane >> 3;
+      const int pre = (g > 0 ? c0 : 0) + (g > 1 ? c1 : 0) + (g > 2 ? c2 : 0);
+      if (lane == 0) s_wtot[warp] = c0 + c1 + c2 + c3;
+      __syncthreads();
+      int base = 0, tot = 0;
+#pragma unroll
+      for (int w4 = 0; w4 < kQW / 4; ++w4) {
+        const int4 v = *reinterpret_cast<const int4*>(&s_wtot[4 * w4]);
+        const int vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { base += (4 * w4 + j < warp) ? vv[j] : 0; tot += vv[j]; }
+      }
+      nact = tot;
+      const int lo = (tot * rank) >> lnc, hi = (tot * (rank + 1)) >> lnc;
+      n_my = hi - lo; lo_my = lo;
+      if (nib) {
+        int slot = base + pre + __popc(wd & ((1u << qsh) - 1u));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (nib & (1u << j)) {
+            if (slot >= lo && slot < hi) s_list[slot - lo] = (unsigned short)(qcell + j);
+            ++slot;
+          }
+        }
+      }
+    }
+    // ---- A0: inactive cells of my band: per-channel sums of the gated gradient --------------------------------------
+    float s1 = 0.f, s2 = 0.f;
+    {
+      float acc0 = 0.f;                      // channel c (= tid & 15), cells (tid >> 4) + 32 j of the band
+#pragma unroll 4
+      for (int cl = tid >> 4; cl < nband; cl += kQT / C) {
+        const int cell = band_lo + cl;
+        const bool act = (s_bAct[cell >> 5] >> (cell & 31)) & 1u;
+        float g = sG[cl * C + c];
+        if (c == 3 && !((s_bPost[cell >> 5] >> (cell & 31)) & 1u)) g = 0.f;
+        acc0 += act ? 0.f : g;
+      }
+      acc0 += __shfl_xor_sync(0xffffffffu, acc0, 16);
+      if (lane < C) s_chs[warp][0][lane] = acc0;
+    }
+    __syncthreads();
+    if (warp == 0 && lane < C) {
+      float ac = 0.f;
+      for (int w = 0; w < kQW; ++w) ac += s_chs[w][0][lane];
+      const float gzs = ac * s_aff[2][lane];          // sum over the inactive cells of gz for this channel
+      if (gn) {
+        const float gu = gzs * gam_c;                 // lane == c here
+        s1 = gu; s2 = gu * uh0;
+        dgam += gzs * uh0; dbet += gzs;
+      }
+    }
+    // ---- A: my active cells: gz = gated g * eta * (1 - tanh^2(gn(u)))  (ncagraph.py:153-166 backward) -------------
+    const float sc_c = s_aff[0][c], bi_c = s_aff[1][c];
+    const float* gin = Gs[cur];
+    const size_t rec_base = ((size_t)t * a.B + b) * HW;
+#pragma unroll 1
+    for (int sl = warp * CPL + hwi; sl < n_my; sl += kQW * CPL) {
+      const int cell = s_list[sl];
+      float g = __ldcg(gin + (size_t)cell * C + c);
+      if (c == 3 && !((s_bPost[cell >> 5] >> (cell & 31)) & 1u)) g = 0.f;
+      const float u = __ldcg(R.rec + (rec_base + lo_my + sl) * kRecStride + kRecU + c);
+      const float th = tanhf(fmaf(u, sc_c, bi_c));
+      const float gz = g * eta * (1.f - th * th);
+      float* dst = sl < R.ucap ? sGZ + sl * C + c : over + (size_t)(sl - R.ucap) * C + c;
+      *dst = gz;
+      if (gn) {
+        const float uh = (u - mu) * rstd, gu = gz * gam_c;
+        s1 += gu; s2 = fmaf(gu, uh, s2);
+        dgam = fmaf(gz, uh, dgam); dbet += gz;
+      }
+    }
+    // ---- S1, S2: warp -> block -> every CTA of the cluster ---------------------------------------------------------
+    {
+      const float f1 = warp_sum(s1), f2 = warp_sum(s2);
+      if (lane == 0) { s_wred[warp][0] = f1; s_wred[warp][1] = f2; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float t1 = lane < kQW ? s_wred[lane][0] : 0.f, t2 = lane < kQW ? s_wred[lane][1] : 0.f;
+      t1 = warp_sum(t1); t2 = warp_sum(t2);
+      if (lane < NC) {
+        float* dst = cluster.map_shared_rank(&s_parts[0][0], lane);
+        dst[rank * 2] = t1; dst[rank * 2 + 1] = t2;
+      }
+    }
+    cl_sync_all();                                                            // ---- cluster barrier 1
+    float s1n = 0.f, s2n = 0.f;
+    if (gn) {
+      for (int r = 0; r < NC; ++r) { s1n += s_parts[r][0]; s2n += s_parts[r][1]; }
+      s1n *= R.inv_n; s2n *= R.inv_n;
+    }
+    // ---- B: tiles of G cells -----------------------------------------------------------------------------------------
+    const int ntiles = (n_my + G - 1) / G;
+#pragma unroll 1
+    for (int tile = warp; tile < ntiles; tile += kQW) {
+      const int slot0 = tile * G;
+      float gxs[MPL];
+      int cellr[MPL];
+      bool valid[MPL];
+#pragma unroll
+      for (int r = 0; r < MPL; ++r) {
+        const int m = hwi + CPL * r, sl = slot0 + m;
+        valid[r] = sl < n_my;
+        const int slc = min(sl, n_my - 1);
+        cellr[r] = s_list[slc];
+        float* rc = R.rec + (rec_base + lo_my + slc) * kRecStride;
+        myY[c * G + m] = __ldcg(rc + c);
+        myY[(C + c) * G + m] = __ldcg(rc + C + c);
+        myY[(2 * C + c) * G + m] = __ldcg(rc + 2 * C + c);
+        const float gz = slc < R.ucap ? sGZ[slc * C + c] : over[(size_t)(slc - R.ucap) * C + c];
+        float gd = gz;
+        if (gn) {
+          const float uh = (__ldcg(rc + kRecU + c) - mu) * rstd;
+          gd = rstd * (gz * gam_c - s1n - uh * s2n);
+        }
+        gd = valid[r] ? gd : 0.f;
+        myGD[c * G + m] = gd;
+        float gm = 0.f;
+        if (msg_on && c >= c_lo) {
+          const float th = __ldcg(rc + kRecTh + c);
+          gm = gd * gain_m * (1.f - th * th);
+        }
+        if (valid[r]) { rc[kRecU + c] = gd; rc[kRecTh + c] = gm; }           // record now holds gd | gm (weight gradients)
+        float acc = 0.f;                                                     // g_xs[c] = sum_cc Wm[cc][c] gm[cc]
+        if (msg_on) {
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc) acc = fmaf(wmT[cc], __shfl_sync(0xffffffffu, gm, (lane & 16) | cc), acc);
+        }
+        gxs[r] = acc;
+      }
+      __syncwarp();
+      // hidden pre-activations of my 4 units (recomputed): acc1[m][jj]
+      float acc1[G][4];
+      {
+        const float4 bb = *reinterpret_cast<const float4*>(sb1 + 4 * lane);
+#pragma unroll
+        for (int m = 0; m < G; ++m) { acc1[m][0] = bb.x; acc1[m][1] = bb.y; acc1[m][2] = bb.z; acc1[m][3] = bb.w; }
+#pragma unroll 8
+        for (int kk = 0; kk < C3; ++kk) {
+          const float4 w = *reinterpret_cast<const float4*>(sW1T + kk * HID + 4 * lane);
+          const float4 yv = *reinterpret_cast<const float4*>(myY + kk * G);
+          const float ym[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+          for (int m = 0; m < G; ++m) {
+            acc1[m][0] = fmaf(ym[m], w.x, acc1[m][0]); acc1[m][1] = fmaf(ym[m], w.y, acc1[m][1]);
+            acc1[m][2] = fmaf(ym[m], w.z, acc1[m][2]); acc1[m][3] = fmaf(ym[m], w.w, acc1[m][3]);
+          }
+        }
+      }
+      // gh[m][jj] = [h > 0] * sum_c W2[c][j] gd[c][m]
+      float gh[G][4];
+#pragma unroll
+      for (int m = 0; m < G; ++m)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) gh[m][jj] = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < C / 4; ++c4) {
+        float4 w2[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) w2[jj] = *reinterpret_cast<const float4*>(sW2P + (lane + 32 * jj) * kQW2S + 4 * c4);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float4 gv = *reinterpret_cast<const float4*>(myGD + (4 * c4 + cc) * G);
+          const float gm4[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float wv = cc == 0 ? w2[jj].x : cc == 1 ? w2[jj].y : cc == 2 ? w2[jj].z : w2[jj].w;
+#pragma unroll
+            for (int m = 0; m < G; ++m) gh[m][jj] = fmaf(wv, gm4[m], gh[m][jj]);
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < G; ++m)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) gh[m][jj] = acc1[m][jj] > 0.f ? gh[m][jj] : 0.f;
+      // gy[kk][m] = sum_j W1[j][kk] gh[j][m]: per 16-channel block a shuffle reduce-scatter that leaves
+      // (cell hwi+2e, channel c) in this lane; block 0 = identity part, 1 = sobel_x part, 2 = sobel_y part
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb) {
+        float pv[4 * C];
+#pragma unroll
+        for (int kc = 0; kc < C; ++kc) {
+          const float4 w = *reinterpret_cast<const float4*>(sW1T + (kb * C + kc) * HID + 4 * lane);
+#pragma unroll
+          for (int m = 0; m < G; ++m) {
+            const int idx = (m & 1) * (2 * C) + kc * 2 + (m >> 1);
+            pv[idx] = fmaf(w.x, gh[m][0], fmaf(w.y, gh[m][1], fmaf(w.z, gh[m][2], w.w * gh[m][3])));
+          }
+        }
+#define REPB_RS_STAGE(N2, SH)                                                         \
+        {                                                                             \
+          const bool upper = (lane & SH) != 0;                                        \
+          _Pragma("unroll") for (int i = 0; i < (N2); ++i) {                          \
+            const float send = upper ? pv[i] : pv[i + (N2)];                          \
+            const float keep = upper ? pv[i + (N2)] : pv[i];                          \
+            pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, SH);                    \
+          }                                                                           \
+        }
+        REPB_RS_STAGE(32, 16) REPB_RS_STAGE(16, 8) REPB_RS_STAGE(8, 4) REPB_RS_STAGE(4, 2) REPB_RS_STAGE(2, 1)
+#undef REPB_RS_STAGE
+#pragma unroll
+        for (int e = 0; e < MPL; ++e)
+          if (valid[e]) RGs[(size_t)cellr[e] * 64 + kb * C + c] = pv[e];
+      }
+#pragma unroll
+      for (int r = 0; r < MPL; ++r)
+        if (valid[r]) RGs[(size_t)cellr[r] * 64 + 3 * C + c] = gxs[r];
+      __syncwarp();
+    }
+    cl_sync_all();                                                            // ---- cluster barrier 2: RG visible
+    // ---- C: my band: g_t = gated g_{t+1} + perception^T (gy of active neighbours) + message^T (g_xs of receivers) --
+    {
+      float* gout = Gs[cur ^ 1];
+      const float wuni = k > 0 ? 1.0f / (float)k : 0.f;
+      auto actbit = [&](int cell) -> bool { return (s_bAct[cell >> 5] >> (cell & 31)) & 1u; };
+#pragma unroll 1
+      for (int it = tid; it < nband * 4; it += kQT) {
+        const int cl = it >> 2, cq = it & 3;
+        const int cell = band_lo + cl, py = cell / W, px = cell - py * W;
+        float4 g = *reinterpret_cast<const float4*>(sG + cl * C + 4 * cq);
+        if (cq == 0 && !((s_bPost[cell >> 5] >> (cell & 31)) & 1u)) g.w = 0.f;
+#pragma unroll
+        for (int ay = -1; ay <= 1; ++ay) {
+#pragma unroll
+          for (int ax = -1; ax <= 1; ++ax) {
+            const int yy = py + ay, xx = px + ax;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const int ac = yy * W + xx;
+            if (!actbit(ac)) continue;
+            const float* rg = RGs + (size_t)ac * 64 + 4 * cq;
+            const float kx = (ax == 0 ? 0.f : (ax > 0 ? 1.f : -1.f)) * (ay == 0 ? 2.f : 1.f);
+            const float ky = (ay == 0 ? 0.f : (ay > 0 ? 1.f : -1.f)) * (ax == 0 ? 2.f : 1.f);
+            if (ay == 0 && ax == 0) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(rg));
+              g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+            }
+            if (kx != 0.f) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(rg + C));
+              g.x = fmaf(kx, v.x, g.x); g.y = fmaf(kx, v.y, g.y); g.z = fmaf(kx, v.z, g.z); g.w = fmaf(kx, v.w, g.w);
+            }
+            if (ky != 0.f) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(rg + 2 * C));
+              g.x = fmaf(ky, v.x, g.x); g.y = fmaf(ky, v.y, g.y); g.z = fmaf(ky, v.z, g.z); g.w = fmaf(ky, v.w, g.w);
+            }
+          }
+        }
+        if (msg_on && (!a2a || ((s_bAS[cell >> 5] >> (cell & 31)) & 1u))) {
+          for (int i = 0; i < k; ++i) {
+            int ry = py + (int)s_off[2 * i], rx = px + (int)s_off[2 * i + 1];
+            ry += ry < 0 ? H : 0; ry -= ry >= H ? H : 0;
+            rx += rx < 0 ? W : 0; rx -= rx >= W ? W : 0;
+            const int rc = ry * W + rx;
+            if (!actbit(rc)) continue;
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(RGs + (size_t)rc * 64 + 3 * C + 4 * cq));
+            g.x = fmaf(wuni, v.x, g.x); g.y = fmaf(wuni, v.y, g.y); g.z = fmaf(wuni, v.z, g.z); g.w = fmaf(wuni, v.w, g.w);
+          }
+        }
+        if (dmg) {
+          const float* D = R.damage + sample_off + cell;
+          g.x *= D[(size_t)(4 * cq) * HW]; g.y *= D[(size_t)(4 * cq + 1) * HW];
+          g.z *= D[(size_t)(4 * cq + 2) * HW]; g.w *= D[(size_t)(4 * cq + 3) * HW];
+        }
+        *reinterpret_cast<float4*>(sG + cl * C + 4 * cq) = g;
+        *reinterpret_cast<float4*>(gout + (size_t)cell * C + 4 * cq) = g;
+      }
+    }
+    cl_sync_all();                                                            // ---- cluster barrier 3: g_t visible
+    cur ^= 1;
+    (void)nact;
+  }
+
+  // dL/dx_0 (NCHW) from my band; per-CTA dgamma / dbeta partials
+  __syncthreads();
+  {
+    const int n8 = (nband + 7) & ~7;
+#pragma unroll 1
+    for (int i = tid; i < n8 * C; i += kQT) {
+      const int ci = i & 7, c4 = (i >> 3) & 3, rest = i >> 5;
+      const int cq = rest & 3, cgp = rest >> 2;
+      const int cl = cgp * 8 + ci, ch = cq * 4 + c4;
+      if (cl < nband) R.g0[sample_off + (size_t)ch * HW + band_lo + cl] = sG[cl * C + ch];
+    }
+  }
+  dgam += __shfl_xor_sync(0xffffffffu, dgam, 16);
+  dbet += __shfl_xor_sync(0xffffffffu, dbet, 16);
+  if (lane < C) { s_chs[warp][0][lane] = dgam; s_chs[warp][1][lane] = dbet; }
+  __syncthreads();
+  if (tid < 2 * C) {
+    const int which = tid / C, ch = tid % C;
+    float ac = 0.f;
+    for (int w = 0; w < kQW; ++w) ac += s_chs[w][which][ch];
+    R.affpart[(size_t)blockIdx.x * 2 * C + tid] = ac;
+  }
+  cl_sync_all();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradients from the records, all steps at once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWT = 256;          // threads
+constexpr int kWNB = 64;          // records per batch
+constexpr int kWNBP = kWNB + 4;
+
+struct WgradArgs {
+  const float* rec;
+  const uint32_t* masks;
+  const int32_t* steps;       // [B] or null
+  int T, B, HW, NW;
+  uint32_t flags;
+  float* wpart;               // [gridDim.x][wtotal]
+  int64_t wtotal;
+  gnca_layout L;
+};
+
+__device__ __forceinline__ float dot4f(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+template <int C>
+__global__ void __launch_bounds__(kWT) k_rep_wgrad(WgradArgs A, Packed P, const float* __restrict__ packed) {
+  constexpr int C3 = 3 * C, HID = 128, NB = kWNB, NBP = kWNBP;
+  constexpr int TK = 6, KG = C3 / TK;          // dW1 tile: 4 hidden units x 6 inputs per thread (JQ*KG = 32*8 = 256 threads)
+  constexpr int JQ = HID / 4;
+  static_assert(JQ * KG == kWT, "dW1 tiling");
+  const bool graph = (A.flags & GNCA_F_GRAPH) != 0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sW1T = reinterpret_cast<float*>(smem_raw);     // [3C][HID]
+  float* sb1 = sW1T + C3 * HID;
+  float* sW2 = sb1 + HID;                               // [C][HID]
+  float* Yt = sW2 + C * HID;                            // [3C][NBP]
+  float* GDt = Yt + C3 * NBP;                           // [C][NBP]
+  float* XSt = GDt + C * NBP;                           // [C][NBP]
+  float* GMt = XSt + C * NBP;                           // [C][NBP]
+  float* ASv = GMt + C * NBP;                           // [NBP]
+  float* Ht = ASv + NBP;                                // [HID][NBP]
+  float* GHt = Ht + HID * NBP;                          // [HID][NBP]
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x;
+  block_copy(sW1T, packed + P.w1t, C3 * HID);
+  block_copy(sb1, packed + P.b1, HID);
+  block_copy(sW2, packed + P.w2, C * HID);
+
+  // persistent accumulators
+  float aW1[4][TK], ab1[4], aW2[2][4], aWm = 0.f, abm = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) { ab1[jj] = 0.f; for (int kk = 0; kk < TK; ++kk) aW1[jj][kk] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) for (int jj = 0; jj < 4; ++jj) aW2[i][jj] = 0.f;
+  const int kg = tid % KG, jg = tid / KG;               // dW1: j = jg + JQ*jj, k = kg + KG*kk
+  const int cq2 = tid % (C / 2), jg2 = tid / (C / 2);   // dW2: c = cq2 + 8*i, j = jg2 + JQ*jj   (8 * 32 = 256 threads)
+  const int mc = tid / C, mci = tid % C;                // dWm[mc][mci]
+
+  const int nseg = A.T * A.B;
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    const int t = seg / A.B, b = seg - t * A.B;
+    if (A.steps && A.steps[b] <= t) continue;
+    __syncthreads();
+    if (tid < 32) {
+      int cnt = 0;
+      const uint32_t* mk = A.masks + ((size_t)seg * 3 + 1) * kMaskWords;
+      for (int i = tid; i < A.NW; i += 32) cnt += __popc(mk[i]);
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (tid == 0) s_cnt = cnt;
+    }
+    __syncthreads();
+    const int nrec = s_cnt;
+    const float* rbase = A.rec + (size_t)seg * A.HW * kRecStride;
+    for (int base = 0; base < nrec; base += NB) {
+      const int nb = min(NB, nrec - base);
+      __syncthreads();                                   // previous batch fully consumed
+      // stage: record-major global -> feature-major smem (zero padded to NB)
+      for (int i = tid; i < NB * kRecStride; i += kWT) {
+        const int cl = i / kRecStride, f = i - cl * kRecStride;
+        const float v = cl < nb ? __ldg(rbase + (size_t)(base + cl) * kRecStride + f) : 0.f;
+        if (f < C3) Yt[f * NBP + cl] = v;
+        else if (f < kRecXs) GDt[(f - kRecU) * NBP + cl] = v;
+        else if (f < kRecTh) XSt[(f - kRecXs) * NBP + cl] = v;
+        else if (f < kRecAs) GMt[(f - kRecTh) * NBP + cl] = v;
+        else if (f == kRecAs) ASv[cl] = v;
+      }
+      __syncthreads();
+      // G1/G2: h = relu(W1 y + b1), gh = (W2^T gd) * [h > 0]
+      {
+        constexpr int CG = NB / 4, JGn = kWT / CG;       // 16 cell groups x 16 hidden groups
+        const int cgp = tid % CG, jg0 = tid / CG;
+        for (int jt = jg0; jt * 4 < HID; jt += JGn) {
+          const int j = jt * 4;
+          float acc[4][4], g2[4][4];
+          const float4 bb = *reinterpret_cast<const float4*>(sb1 + j);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            acc[m][0] = bb.x; acc[m][1] = bb.y; acc[m][2] = bb.z; acc[m][3] = bb.w;
+            g2[m][0] = g2[m][1] = g2[m][2] = g2[m][3] = 0.f;
+          }
+#pragma unroll 4
+          for (int kk = 0; kk < C3; ++kk) {
+            const float4 yv = *reinterpret_cast<const float4*>(Yt + kk * NBP + 4 * cgp);
+            const float4 w = *reinterpret_cast<const float4*>(sW1T + kk * HID + j);
+            const float ym[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              acc[m][0] = fmaf(ym[m], w.x, acc[m][0]); acc[m][1] = fmaf(ym[m], w.y, acc[m][1]);
+              acc[m][2] = fmaf(ym[m], w.z, acc[m][2]); acc[m][3] = fmaf(ym[m], w.w, acc[m][3]);
+            }
+          }
+#pragma unroll 4
+          for (int cc = 0; cc < C; ++cc) {
+            const float4 gv = *reinterpret_cast<const float4*>(GDt + cc * NBP + 4 * cgp);
+            const float4 w = *reinterpret_cast<const float4*>(sW2 + cc * HID + j);
+            const float gm[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              g2[m][0] = fmaf(gm[m], w.x, g2[m][0]); g2[m][1] = fmaf(gm[m], w.y, g2[m][1]);
+              g2[m][2] = fmaf(gm[m], w.z, g2[m][2]); g2[m][3] = fmaf(gm[m], w.w, g2[m][3]);
+            }
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float4 hv, gv;
+            hv.x = fmaxf(acc[0][jj], 0.f); hv.y = fmaxf(acc[1][jj], 0.f);
+            hv.z = fmaxf(acc[2][jj], 0.f); hv.w = fmaxf(acc[3][jj], 0.f);
+            gv.x = acc[0][jj] > 0.f ? g2[0][jj] : 0.f; gv.y = acc[1][jj] > 0.f ? g2[1][jj] : 0.f;
+            gv.z = acc[2][jj] > 0.f ? g2[2][jj] : 0.f; gv.w = acc[3][jj] > 0.f ? g2[3][jj] : 0.f;
+            *reinterpret_cast<float4*>(Ht + (j + jj) * NBP + 4 * cgp) = hv;
+            *reinterpret_cast<float4*>(GHt + (j + jj) * NBP + 4 * cgp) = gv;
+          }
+        }
+      }
+      __syncthreads();
+      // dW1 += GH^T Y, db1 += colsum(GH)   (padding cells have gd = 0 -> gh = 0)
+      for (int c4 = 0; c4 < NB / 4; ++c4) {
+        float4 g[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) g[jj] = *reinterpret_cast<const float4*>(GHt + (jg + JQ * jj) * NBP + 4 * c4);
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+          const float4 yv = *reinterpret_cast<const float4*>(Yt + (kg + KG * kk) * NBP + 4 * c4);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) aW1[jj][kk] += dot4f(g[jj], yv);
+        }
+        if (kg == 0) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) ab1[jj] += (g[jj].x + g[jj].y) + (g[jj].z + g[jj].w);
+        }
+      }
+      // dW2 += GD^T H
+      for (int c4 = 0; c4 < NB / 4; ++c4) {
+        float4 hh[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) hh[jj] = *reinterpret_cast<const float4*>(Ht + (jg2 + JQ * jj) * NBP + 4 * c4);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float4 gv = *reinterpret_cast<const float4*>(GDt + (cq2 + (C / 2) * i) * NBP + 4 * c4);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) aW2[i][jj] += dot4f(gv, hh[jj]);
+        }
+      }
+      // dWm += GM^T XS, dbm += GM . AS   (graph_augmentation.py:57 msg_proj)
+      if (graph) {
+        for (int c4 = 0; c4 < NB / 4; ++c4) {
+          const float4 gmv = *reinterpret_cast<const float4*>(GMt + mc * NBP + 4 * c4);
+          const float4 xv = *reinterpret_cast<const float4*>(XSt + mci * NBP + 4 * c4);
+          aWm += dot4f(gmv, xv);
+          if (mci == 0) abm += dot4f(gmv, *reinterpret_cast<const float4*>(ASv + 4 * c4));
+        }
+      }
+    }
+  }
+  // one partial per block (canonical layout); the block's row was zeroed by the launcher
+  float* wp = A.wpart + (size_t)blockIdx.x * A.wtotal;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = jg + JQ * jj;
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) wp[A.L.w1 + (int64_t)j * C3 + (kg + KG * kk)] = aW1[jj][kk];
+    if (kg == 0) wp[A.L.b1 + j] = ab1[jj];
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) wp[A.L.w2 + (int64_t)(cq2 + (C / 2) * i) * HID + (jg2 + JQ * jj)] = aW2[i][jj];
+  if (graph) {
+    wp[A.L.wm + mc * C + mci] = aWm;
+    if (mci == 0) wp[A.L.bm + mc] = abm;
+  }
+}
+
+// gparams[i] += sum over blocks of wpart[blk][i] (fixed order); + dgamma / dbeta partials of the resident kernel
+__global__ void k_rep_wreduce(int nblk, int64_t total, const float* __restrict__ wpart, int naff, int C,
+                              const float* __restrict__ affpart, gnca_layout L, float* __restrict__ gparams) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float acc = 0.f;
+  for (int bl = 0; bl < nblk; ++bl) acc += wpart[(size_t)bl * total + i];
+  if (i >= L.gamma && i < L.gamma + C) for (int r = 0; r < naff; ++r) acc += affpart[(size_t)r * 2 * C + (i - L.gamma)];
+  if (i >= L.beta && i < L.beta + C) for (int r = 0; r < naff; ++r) acc += affpart[(size_t)r * 2 * C + C + (i - L.beta)];
+  gparams[i] += acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+static size_t rep_bwd_smem_bytes(int C, int HW, int NC, int ucap) {
+  const int bandcap = ((HW + NC - 1) / NC) + 1;
+  size_t f = (size_t)3 * C * 128 + 128 + 128 * kQW2S + (size_t)bandcap * C + (size_t)ucap * C + (size_t)kQW * 3 * C * kQG +
+             (size_t)kQW * C * kQG;
+  return f * sizeof(float) + (size_t)((bandcap + 7) & ~7) * sizeof(unsigned short) + 32;
+}
+
+size_t rep_bptt_bytes(const gnca_model& m, int B, int H, int W, int T) {
+  if (m.C != 16 || m.hidden != 128 || H > 64 || W > 64 || W < 4 || (W & 3) || H * W > 2048) return 0;
+  const size_t HW = (size_t)H * W;
+  size_t bytes = (size_t)T * B * HW * kRecStride * sizeof(float);
+  bytes = (bytes + 255) & ~(size_t)255;
+  bytes += (size_t)T * B * 3 * kMaskWords * sizeof(uint32_t);
+  bytes += (size_t)T * B * 2 * sizeof(float) + 256;
+  return bytes;
+}
+
+void rep_bptt_carve(void* base, int B, int H, int W, int T, float** rec, uint32_t** masks, float** stats) {
+  const size_t HW = (size_t)H * W;
+  char* p = reinterpret_cast<char*>(base);
+  size_t o = (size_t)T * B * HW * kRecStride * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  *rec = reinterpret_cast<float*>(p);
+  *masks = reinterpret_cast<uint32_t*>(p + o);
+  o += (size_t)T * B * 3 * kMaskWords * sizeof(uint32_t);
+  *stats = reinterpret_cast<float*>(p + o);
+}
+
+size_t rep_bwd_workspace_bytes(const gnca_model& m, int B, int H, int W) {
+  const size_t HW = (size_t)H * W, C = m.C;
+  size_t f = 2 * (size_t)B * HW * C + (size_t)B * HW * 64 + (size_t)B * HW * C /*over*/ + (size_t)B * 8 * 2 * C;
+  const gnca_layout L = make_layout(m);
+  f += (size_t)kMaxWgradBlocks * (size_t)L.total;
+  return f * sizeof(float) + 1024;
+}
+
+int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,
+                const gnca_schedule& sched, void* bptt, const float* gT, float* g0, float* gparams, void* workspace,
+                cudaStream_t st) {
+  const bool graph = (m.flags & GNCA_F_GRAPH) != 0;
+  if (rep_bptt_bytes(m, B, H, W, sched.T) == 0) return GNCA_ERR_UNSUPPORTED;
+  const int k = graph ? sched.k : 0;
+  if (graph && k > 0 && !(m.flags & GNCA_F_TORUS)) return GNCA_ERR_UNSUPPORTED;
+  if (k > 16) return GNCA_ERR_UNSUPPORTED;
+  const int C = 16, HW = H * W;
+  float *rec, *stats;
+  uint32_t* masks;
+  rep_bptt_carve(bptt, B, H, W, sched.T, &rec, &masks, &stats);
+  const gnca_layout L = make_layout(m);
+  float* ws = reinterpret_cast<float*>(workspace);
+  float* Gbuf = ws; ws += 2 * (size_t)B * HW * C;
+  float* RG = ws; ws += (size_t)B * HW * 64;
+  float* over = ws; ws += (size_t)B * HW * C;
+  float* affpart = ws; ws += (size_t)B * 8 * 2 * C;
+  float* wpart = ws;
+
+  RepBwdArgs R{};
+  fill_step_args(R.s, m, B, H, W);
+  R.s.k = k;
+  R.s.message_gain_dev = sched.message_gain;
+  R.s.offsets_dev = sched.offsets;
+  R.s.steps = sched.steps;
+  R.T = sched.T;
+  R.inv_n = (float)(1.0 / ((double)C * (double)H * (double)W));
+  R.rec = rec; R.masks = masks; R.stats = stats; R.gT = gT; R.g0 = g0; R.Gbuf = Gbuf; R.RG = RG; R.over = over;
+  R.affpart = affpart;
+  R.damage = sched.damage; R.damage_step = sched.damage_step;
+
+  const char* env_nc = getenv("GNCA_RESIDENT_NC");
+  const int cands[4] = {8, 4, 2, 1};
+  int pick = -1, pick_ucap = 0;
+  size_t pick_smem = 0;
+  for (int pass = 0; pass < 2 && pick < 0; ++pass) {
+    for (int ci = (pass == 0 ? 0 : 3); ci >= 0 && ci < 4; ci += (pass == 0 ? 1 : -1)) {
+      const int NC = cands[ci];
+      if (env_nc && atoi(env_nc) != NC) continue;
+      const int share = (HW + NC - 1) / NC + 1;
+      int ucap = share < 512 ? share : 512;
+      size_t smem = rep_bwd_smem_bytes(C, HW, NC, ucap);
+      while (smem > 226 * 1024 && ucap > 128) { ucap -= 64; smem = rep_bwd_smem_bytes(C, HW, NC, ucap); }
+      if (smem > 226 * 1024) continue;
+      GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(B * NC); q.blockDim = dim3(kQT); q.dynamicSmemBytes = smem; q.stream = st;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = NC; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, k_rep_bwd<16>, &q) != cudaSuccess || ncl < 1) {
+        cudaGetLastError();
+        continue;
+      }
+      if (pass == 0 && B > ncl && !env_nc) continue;
+      pick = NC; pick_ucap = ucap; pick_smem = smem;
+      break;
+    }
+  }
+  if (pick < 0) return GNCA_ERR_UNSUPPORTED;
+  R.NC = pick; R.ucap = pick_ucap;
+  {
+    const int share = (HW + pick - 1) / pick + 1;
+    R.over_cap = share > pick_ucap ? share - pick_ucap : 0;
+  }
+  if (getenv("GNCA_DEBUG"))
+    fprintf(stderr, "[gnca] resident bwd: B=%d NC=%d ucap=%d over=%d smem=%zu\n", B, pick, R.ucap, R.over_cap, pick_smem);
+  GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pick_smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(B * pick);
+  cfg.blockDim = dim3(kQT);
+  cfg.dynamicSmemBytes = pick_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pick; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  prof_begin(PROF_RESIDENT_BWD, st);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_rep_bwd<16>, R, P, packed);
+  prof_end(PROF_RESIDENT_BWD, st);
+  if (e != cudaSuccess) return (int)e;
+  GNCA_LAUNCH_CHECK();
+
+  // weight gradients from the records
+  WgradArgs A{};
+  A.rec = rec; A.masks = masks; A.steps = sched.steps; A.T = sched.T; A.B = B; A.HW = HW; A.NW = (HW + 31) >> 5;
+  A.flags = m.flags; A.wpart = wpart; A.wtotal = L.total; A.L = L;
+  int nseg = sched.T * B;
+  int nblk = nseg < kMaxWgradBlocks ? nseg : kMaxWgradBlocks;
+  if (nblk < 1) nblk = 1;
+  GNCA_CHECK_CUDA(cudaMemsetAsync(wpart, 0, (size_t)nblk * L.total * sizeof(float), st));
+  const size_t wsmem = ((size_t)3 * C * 128 + 128 + (size_t)C * 128 + (size_t)(3 * C + 3 * C) * kWNBP + kWNBP +
+                        2 * (size_t)128 * kWNBP) * sizeof(float);
+  GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_wgrad<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+  prof_begin(PROF_BWD_MLP, st);
+  k_rep_wgrad<16><<<nblk, kWT, wsmem, st>>>(A, P, packed);
+  prof_end(PROF_BWD_MLP, st);
+  GNCA_LAUNCH_CHECK();
+  k_rep_wreduce<<<(int)((L.total + 255) / 256), 256, 0, st>>>(nblk, L.total, wpart, B * pick, C, affpart, L, gparams);
+  GNCA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace gnca

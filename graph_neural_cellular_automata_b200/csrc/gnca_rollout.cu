@@ -68,7 +68,9 @@ extern "C" {
 size_t gnca_rollout_workspace_bytes(const gnca_model* m, int B, int H, int W, int T) {
   (void)T;
   if (!m || B <= 0 || H <= 0 || W <= 0) return 0;
-  return carve_rollout(nullptr, *m, B, H, W).bytes;
+  const size_t a = carve_rollout(nullptr, *m, B, H, W).bytes;
+  const size_t b = (m->C == 16) ? rep_bwd_workspace_bytes(*m, B, H, W) : 0;
+  return a > b ? a : b;
 }
 
 int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H, int W, const gnca_schedule* sched,
@@ -97,7 +99,7 @@ int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H,
       int rc = GNCA_ERR_UNSUPPORTED;
       if (impl != 3 && !(kind && kind[0] == 'b'))
         rc = run_rep_fwd(*m, P, packed_dev, B, H, W, *sched, x0_dev, xT_dev, x_hist_dev, stats_hist_dev, u_hist_dev,
-                         r.ping, st);
+                         nullptr, nullptr, r.ping, st);
       if (rc == GNCA_ERR_UNSUPPORTED)
         rc = run_resident_fwd(*m, P, packed_dev, B, H, W, *sched, x0_dev, xT_dev, x_hist_dev, stats_hist_dev,
                               u_hist_dev, r.ping, r.pong, r.alpha_tmp, st);
@@ -187,4 +189,57 @@ int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H,
   return 0;
 }
 
+
+/* ---- resident BPTT: records instead of the dense x_t / u_t history (gnca_rep.cu / gnca_rep_bwd.cu) ---- */
+size_t gnca_bptt_bytes(const gnca_model* m, int B, int H, int W, int T) {
+  if (!m || B <= 0 || H <= 0 || W <= 0 || T < 0) return 0;
+  if ((m->flags & GNCA_F_GRAPH) && !(m->flags & GNCA_F_TORUS)) return 0;
+  return rep_bptt_bytes(*m, B, H, W, T);
+}
+
+int gnca_rollout_fwd_bptt(const gnca_model* m, const float* packed_dev, int B, int H, int W, const gnca_schedule* sched,
+                          const float* x0_dev, float* xT_dev, float* x_hist_dev, void* bptt_dev, size_t bptt_bytes,
+                          void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!m || !packed_dev || !sched || !x0_dev || !xT_dev || !bptt_dev || !workspace_dev) return GNCA_ERR_ARG;
+  if (B <= 0 || H <= 0 || W <= 0 || sched->T < 0) return GNCA_ERR_ARG;
+  if (!model_supported(*m)) return GNCA_ERR_UNSUPPORTED;
+  const size_t need = gnca_bptt_bytes(m, B, H, W, sched->T);
+  if (need == 0) return GNCA_ERR_UNSUPPORTED;
+  if (need > bptt_bytes) return GNCA_ERR_WORKSPACE;
+  RolloutWorkspace r = carve_rollout(workspace_dev, *m, B, H, W);
+  if (r.bytes > workspace_bytes) return GNCA_ERR_WORKSPACE;
+  const bool graph = (m->flags & GNCA_F_GRAPH) != 0;
+  const Packed P = make_packed(m->C, m->hidden, m->d_model, graph);
+  float *rec, *stats;
+  uint32_t* masks;
+  rep_bptt_carve(bptt_dev, B, H, W, sched->T, &rec, &masks, &stats);
+  if (sched->T == 0) {
+    cudaMemcpyAsync(xT_dev, x0_dev, (size_t)B * m->C * H * W * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (x_hist_dev)
+      cudaMemcpyAsync(x_hist_dev, x0_dev, (size_t)B * m->C * H * W * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return 0;
+  }
+  return run_rep_fwd(*m, P, packed_dev, B, H, W, *sched, x0_dev, xT_dev, x_hist_dev, stats, nullptr, rec, masks, r.ping,
+                     (cudaStream_t)stream);
+}
+
+int gnca_rollout_bwd_bptt(const gnca_model* m, const float* packed_dev, int B, int H, int W, const gnca_schedule* sched,
+                          void* bptt_dev, size_t bptt_bytes, const float* gT_dev, float* g0_dev, float* gparams_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!m || !packed_dev || !sched || !bptt_dev || !gT_dev || !g0_dev || !gparams_dev || !workspace_dev) return GNCA_ERR_ARG;
+  if (B <= 0 || H <= 0 || W <= 0 || sched->T < 0) return GNCA_ERR_ARG;
+  if (!model_supported(*m)) return GNCA_ERR_UNSUPPORTED;
+  const size_t need = gnca_bptt_bytes(m, B, H, W, sched->T);
+  if (need == 0) return GNCA_ERR_UNSUPPORTED;
+  if (need > bptt_bytes) return GNCA_ERR_WORKSPACE;
+  if (rep_bwd_workspace_bytes(*m, B, H, W) > workspace_bytes) return GNCA_ERR_WORKSPACE;
+  const bool graph = (m->flags & GNCA_F_GRAPH) != 0;
+  const Packed P = make_packed(m->C, m->hidden, m->d_model, graph);
+  if (sched->T == 0) {
+    cudaMemcpyAsync(g0_dev, gT_dev, (size_t)B * m->C * H * W * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return 0;
+  }
+  return run_rep_bwd(*m, P, packed_dev, B, H, W, *sched, bptt_dev, gT_dev, g0_dev, gparams_dev, workspace_dev,
+                     (cudaStream_t)stream);
+}
 }  // extern "C"

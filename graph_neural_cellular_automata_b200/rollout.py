@@ -166,39 +166,57 @@ def make_schedule(model, B: int, H: int, W: int, T: int, *, fire_rate: Union[flo
 
 
 class History:
-    """What the forward keeps for BPTT: x_t for every step, and (optionally) the masked pre-norm update of the
-    active cells + the GroupNorm statistics so that the backward does not re-run the forward MLP."""
+    """What the forward keeps for BPTT.  Two formats:
+    * records (`bptt`): the replicated-state kernel's per-active-cell records + bitmaps + statistics -- consumed by the
+      cluster-resident backward (gnca_rollout_bwd_bptt); `x` is only filled when the caller asked for the history;
+    * dense: x_t for every step and (optionally) the masked pre-norm update of the active cells + the GroupNorm
+      statistics, consumed by the streaming backward (gnca_rollout_bwd)."""
 
-    def __init__(self, x, u=None, stats=None):
-        self.x, self.u, self.stats = x, u, stats
+    def __init__(self, x, u=None, stats=None, bptt=None, shape=None):
+        self.x, self.u, self.stats, self.bptt = x, u, stats, bptt
+        self._shape = tuple(shape) if shape is not None else tuple(x.shape)
 
     @property
     def shape(self):
-        return self.x.shape
+        return self._shape
 
     def __getitem__(self, i):
         return self.x[i]
 
 
+BPTT_MAX_BYTES = 48 << 30      # above this the record buffer is not worth it: dense history + streaming backward
+
+
 def rollout_fwd_raw(desc, packed, x0: torch.Tensor, sched: Schedule, *, history: bool, impl: int = 0,
-                    keep_u: bool = True):
-    """gnca_rollout_fwd without autograd: returns (x_T, History or None)."""
+                    keep_u: bool = True, keep_x: bool = True):
+    """gnca_rollout_fwd without autograd: returns (x_T, History or None).  `keep_x=False`: the caller only needs the
+    history for the backward (the resident BPTT path then skips storing x_t)."""
     x0 = GF._require_cuda_f32(x0, "x0")
     B, Cc, H, W = x0.shape
     if Cc != desc.C:
-        raise RuntimeError(f"x0 has {Cc} channels, model has {desc.C}")
+        raise ValueError(f"x0 has {Cc} channels, model has {desc.C}")
     lib = _lib.load()
     T = sched.T
     xT = torch.empty_like(x0)
+    nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, T)
+    ws = GF._WS.get(x0.device, nbytes)
+    cs = sched.c_struct()
+    if history and impl in (0, 2) and T > 0:
+        nb = lib.gnca_bptt_bytes(C.byref(desc), B, H, W, T)
+        if 0 < nb <= BPTT_MAX_BYTES:
+            bptt = torch.empty(nb, dtype=torch.uint8, device=x0.device)
+            hist = torch.empty(T + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device) if keep_x else None
+            rc = lib.gnca_rollout_fwd_bptt(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(x0), GF._ptr(xT),
+                                           GF._ptr(hist), GF._ptr(bptt), nb, GF._ptr(ws), ws.numel(), GF._stream())
+            if rc != _lib.GNCA_ERR_UNSUPPORTED:
+                _lib.check(rc, "gnca_rollout_fwd_bptt")
+                return xT, History(hist, bptt=bptt, shape=(T + 1, B, Cc, H, W))
     hist = uh = sh = None
     if history:
         hist = torch.empty(T + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device)
         if keep_u and T > 0:
             uh = torch.empty(T, B, Cc, H, W, dtype=torch.float32, device=x0.device)
             sh = torch.empty(T, B, 2, dtype=torch.float32, device=x0.device)
-    nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, T)
-    ws = GF._WS.get(x0.device, nbytes)
-    cs = sched.c_struct()
     _lib.check(lib.gnca_rollout_fwd(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(x0), GF._ptr(xT),
                                     GF._ptr(hist), GF._ptr(sh), GF._ptr(uh), GF._ptr(ws), ws.numel(), int(impl),
                                     GF._stream()), "gnca_rollout_fwd")
@@ -213,13 +231,18 @@ def rollout_bwd_raw(desc, packed, hist, sched: Schedule, gT: torch.Tensor, *, gf
     _, B, Cc, H, W = hist.shape
     gT = GF._require_cuda_f32(gT, "grad_output")
     lib = _lib.load()
-    lay = GF.param_layout(desc)
-    g0 = torch.empty_like(gT)
+    g0 = torch.empty(B, Cc, H, W, dtype=torch.float32, device=gT.device)
     if gflat is None:
+        lay = GF.param_layout(desc)
         gflat = torch.zeros(lay.total, dtype=torch.float32, device=gT.device)
     nbytes = lib.gnca_rollout_workspace_bytes(C.byref(desc), B, H, W, sched.T)
     ws = GF._WS.get(gT.device, nbytes)
     cs = sched.c_struct()
+    if hist.bptt is not None:
+        _lib.check(lib.gnca_rollout_bwd_bptt(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(hist.bptt),
+                                             hist.bptt.numel(), GF._ptr(gT), GF._ptr(g0), GF._ptr(gflat), GF._ptr(ws),
+                                             ws.numel(), GF._stream()), "gnca_rollout_bwd_bptt")
+        return g0, gflat
     _lib.check(lib.gnca_rollout_bwd(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(hist.x),
                                     GF._ptr(hist.stats), GF._ptr(hist.u), GF._ptr(gT), GF._ptr(g0), GF._ptr(gflat),
                                     GF._ptr(ws), ws.numel(), int(impl), GF._stream()), "gnca_rollout_bwd")
@@ -230,7 +253,8 @@ class _RolloutFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x0, cfg, *params):
         xT, hist = rollout_fwd_raw(cfg["desc"], cfg["packed"], x0, cfg["schedule"],
-                                   history=bool(cfg["need_grad"] or cfg["history"]), impl=cfg["impl"])
+                                   history=bool(cfg["need_grad"] or cfg["history"]), impl=cfg["impl"],
+                                   keep_x=bool(cfg["history"]))
         ctx.cfg = cfg
         ctx.param_shapes = [p.shape for p in params]
         ctx.hist = hist

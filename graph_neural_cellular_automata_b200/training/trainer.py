@@ -159,8 +159,8 @@ class GraphNCATrainer:
             sched.damage_step = 0
         x0 = sh.take(state).contiguous()
         desc, packed = self.model.model_desc(), self.model.packed_weights()
-        impl = {"auto": 0, "streaming": 1, "resident": 2}[cfg.rollout_impl]
-        xT, hist = rollout_fwd_raw(desc, packed, x0, sched, history=True, impl=impl)
+        impl = {"auto": 0, "streaming": 1, "resident": 2, "banded": 3}[cfg.rollout_impl]
+        xT, hist = rollout_fwd_raw(desc, packed, x0, sched, history=True, impl=impl, keep_x=False)
         per_local, gxT = premult_loss(xT, self.target, 1.0 / Bg)             # loss = mean over the GLOBAL batch
         _, gflat = rollout_bwd_raw(desc, packed, hist, sched, gxT, impl=impl)
         sh.allreduce_sum_(gflat)                                             # the one data-path collective

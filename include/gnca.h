@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GNCA_VERSION 102
+#define GNCA_VERSION 103
 
 #define GNCA_ERR_ARG (-1)         /* null pointer / bad size */
 #define GNCA_ERR_UNSUPPORTED (-2) /* shape or flag combination without a kernel */
@@ -169,6 +169,24 @@ int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H,
                      const float* u_hist_dev,
                      const float* gT_dev, float* g0_dev, float* gparams_dev,
                      void* workspace_dev, size_t workspace_bytes, int impl, void* stream);
+
+/*
+ * Resident BPTT (16-channel / 128-hidden models, classic or torus graph, grids up to 2048 cells with W % 4 == 0).
+ * Instead of the dense x_t / u_t history the forward keeps one compact record per ACTIVE cell and step (perception,
+ * pre-norm update, gathered sender state ...) plus three bitmaps and the GroupNorm statistics per step, in the opaque
+ * buffer `bptt_dev` (gnca_bptt_bytes; 0 = configuration not supported -> use gnca_rollout_fwd/_bwd).  The backward
+ * is one cluster-resident kernel for the propagation of dL/dx plus one batched pass over all records for the weight
+ * gradients.  x_hist_dev may be NULL (it is not needed by the backward).  gparams_dev is ACCUMULATED into.
+ */
+size_t gnca_bptt_bytes(const gnca_model* m, int B, int H, int W, int T);
+int gnca_rollout_fwd_bptt(const gnca_model* m, const float* packed_dev, int B, int H, int W,
+                          const gnca_schedule* sched, const float* x0_dev, float* xT_dev, float* x_hist_dev,
+                          void* bptt_dev, size_t bptt_bytes, void* workspace_dev, size_t workspace_bytes,
+                          void* stream);
+int gnca_rollout_bwd_bptt(const gnca_model* m, const float* packed_dev, int B, int H, int W,
+                          const gnca_schedule* sched, void* bptt_dev, size_t bptt_bytes, const float* gT_dev,
+                          float* g0_dev, float* gparams_dev, void* workspace_dev, size_t workspace_bytes,
+                          void* stream);
 
 /* ------------------------------------------------------------------ training glue ----------- */
 /* per_sample[b] = mean_{4HW}([rgb*a, a] - target)^2 ; gx (optional) = d(scale * sum_b per_sample[b])/dx, [B,C,H,W] */
