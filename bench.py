@@ -341,11 +341,12 @@ def main():
         torch.cuda.synchronize()
         lib.gnca_profile_enable(0)
         per_kernel = {}
-        for kid, kname in ((0, "k_update"), (1, "k_apply"), (2, "k_resident_fwd"), (3, "k_bwd_mlp"), (6, "k_resident_bwd")):
+        for kid, kname in ((0, "k_update"), (1, "k_apply"), (2, "k_resident_fwd"), (3, "k_bwd_mlp / k_rep_wgrad"), (6, "k_resident_bwd")):
             ms, n = ctypes.c_double(0), ctypes.c_ulonglong(0)
             lib.gnca_profile_read(kid, ctypes.byref(ms), ctypes.byref(n))
             if n.value:
                 per_kernel[kname] = (ms.value, n.value)
+        kernels_ms = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof} for k, v in per_kernel.items()}
         if per_kernel:
             kname = max(per_kernel, key=lambda k: per_kernel[k][0])
             ms, n = per_kernel[kname]
@@ -364,7 +365,7 @@ def main():
                     "hbm_view": {"algorithmic_bytes_per_step": int(2 * x0_host.numel() * 4),
                                  "achieved_GBps": 2 * x0_host.numel() * 4 * nprof / (ms * 1e-3) / 1e9,
                                  "peak_GBps": 6547.8},
-                    "share_of_step": ms / nprof / (dev_ms_max / args.steps)}
+                    "share_of_step": ms / nprof / (dev_ms_max / args.steps), "kernels": kernels_ms}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not cfg["train"]:

@@ -14,7 +14,7 @@ namespace gnca {
 constexpr int kRecY = 0, kRecU = 48, kRecXs = 64, kRecTh = 80, kRecAs = 96, kRecStride = 100;
 // bitmaps of a step: [0] sender-alive (graph_alpha_thr), [1] active = fire & pre-alive, [2] post-alive
 constexpr int kMaskWords = 64;
-// blocks of the batched weight-gradient kernel (one per SM: ~130 KB of shared memory each)
-constexpr int kMaxWgradBlocks = 148;
+// blocks of the batched weight-gradient kernel (two per SM)
+constexpr int kMaxWgradBlocks = 296;
 
 }  // namespace gnca

@@ -497,8 +497,9 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
 // Weight gradients from the records, all steps at once.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWT = 256;          // threads
-constexpr int kWNB = 64;          // records per batch
+constexpr int kWNB = 32;          // records per batch
 constexpr int kWNBP = kWNB + 4;
+constexpr int kWMaxSeg = 256;     // (t, b) segments per block and round
 
 struct WgradArgs {
   const float* rec;
@@ -514,26 +515,35 @@ struct WgradArgs {
 __device__ __forceinline__ float dot4f(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int C>
-__global__ void __launch_bounds__(kWT) k_rep_wgrad(WgradArgs A, Packed P, const float* __restrict__ packed) {
+__global__ void __launch_bounds__(kWT, 2) k_rep_wgrad(WgradArgs A, Packed P, const float* __restrict__ packed) {
   constexpr int C3 = 3 * C, HID = 128, NB = kWNB, NBP = kWNBP;
   constexpr int TK = 6, KG = C3 / TK;          // dW1 tile: 4 hidden units x 6 inputs per thread (JQ*KG = 32*8 = 256 threads)
   constexpr int JQ = HID / 4;
+  constexpr int RAWF = NB * kRecStride;        // floats of one raw batch
   static_assert(JQ * KG == kWT, "dW1 tiling");
+  static_assert((NB / 4) * (HID / 4) == kWT, "G1 tiling: one 4x4 tile per thread");
   const bool graph = (A.flags & GNCA_F_GRAPH) != 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sW1T = reinterpret_cast<float*>(smem_raw);     // [3C][HID]
   float* sb1 = sW1T + C3 * HID;
   float* sW2 = sb1 + HID;                               // [C][HID]
-  float* Yt = sW2 + C * HID;                            // [3C][NBP]
+  float* RAW = sW2 + C * HID;                           // [2][NB][kRecStride] record-major double buffer (cp.async)
+  float* Yt = RAW + 2 * RAWF;                           // [3C][NBP] feature-major
   float* GDt = Yt + C3 * NBP;                           // [C][NBP]
   float* XSt = GDt + C * NBP;                           // [C][NBP]
   float* GMt = XSt + C * NBP;                           // [C][NBP]
   float* ASv = GMt + C * NBP;                           // [NBP]
   float* Ht = ASv + NBP;                                // [HID][NBP]
   float* GHt = Ht + HID * NBP;                          // [HID][NBP]
-  __shared__ int s_cnt;
+  __shared__ int s_cnt[kWMaxSeg];
   const int tid = threadIdx.x;
   block_copy(sW1T, packed + P.w1t, C3 * HID);
   block_copy(sb1, packed + P.b1, HID);
@@ -548,85 +558,108 @@ __global__ void __launch_bounds__(kWT) k_rep_wgrad(WgradArgs A, Packed P, const 
   const int kg = tid % KG, jg = tid / KG;               // dW1: j = jg + JQ*jj, k = kg + KG*kk
   const int cq2 = tid % (C / 2), jg2 = tid / (C / 2);   // dW2: c = cq2 + 8*i, j = jg2 + JQ*jj   (8 * 32 = 256 threads)
   const int mc = tid / C, mci = tid % C;                // dWm[mc][mci]
+  const int cgp = tid % (NB / 4), jt = tid / (NB / 4);  // G1/G2: cells 4cgp.., hidden units 4jt..
 
   const int nseg = A.T * A.B;
-  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-    const int t = seg / A.B, b = seg - t * A.B;
-    if (A.steps && A.steps[b] <= t) continue;
+  for (int seg0 = blockIdx.x; seg0 < nseg; seg0 += gridDim.x * kWMaxSeg) {
+    // record counts of my segments of this round (popcount of the active bitmap)
     __syncthreads();
-    if (tid < 32) {
+    for (int si = tid; si < kWMaxSeg; si += kWT) {
+      const int seg = seg0 + si * gridDim.x;
       int cnt = 0;
-      const uint32_t* mk = A.masks + ((size_t)seg * 3 + 1) * kMaskWords;
-      for (int i = tid; i < A.NW; i += 32) cnt += __popc(mk[i]);
-      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (tid == 0) s_cnt = cnt;
+      if (seg < nseg) {
+        const int t = seg / A.B, b = seg - t * A.B;
+        if (!(A.steps && A.steps[b] <= t)) {
+          const uint32_t* mk = A.masks + ((size_t)seg * 3 + 1) * kMaskWords;
+          for (int i = 0; i < A.NW; ++i) cnt += __popc(__ldg(mk + i));
+        }
+      }
+      s_cnt[si] = cnt;
     }
     __syncthreads();
-    const int nrec = s_cnt;
-    const float* rbase = A.rec + (size_t)seg * A.HW * kRecStride;
-    for (int base = 0; base < nrec; base += NB) {
-      const int nb = min(NB, nrec - base);
-      __syncthreads();                                   // previous batch fully consumed
-      // stage: record-major global -> feature-major smem (zero padded to NB)
-      for (int i = tid; i < NB * kRecStride; i += kWT) {
-        const int cl = i / kRecStride, f = i - cl * kRecStride;
-        const float v = cl < nb ? __ldg(rbase + (size_t)(base + cl) * kRecStride + f) : 0.f;
-        if (f < C3) Yt[f * NBP + cl] = v;
-        else if (f < kRecXs) GDt[(f - kRecU) * NBP + cl] = v;
-        else if (f < kRecTh) XSt[(f - kRecXs) * NBP + cl] = v;
-        else if (f < kRecAs) GMt[(f - kRecTh) * NBP + cl] = v;
-        else if (f == kRecAs) ASv[cl] = v;
+    // flat walk over (segment, batch) with one batch of look-ahead
+    int si = 0, base = 0;
+    auto skip_empty = [&](int& s_, int& b_) { while (s_ < kWMaxSeg && b_ >= s_cnt[s_]) { ++s_; b_ = 0; } };
+    auto issue = [&](int s_, int b_, int buf) {
+      if (s_ < kWMaxSeg) {
+        const int seg = seg0 + s_ * gridDim.x;
+        const int nb = min(NB, s_cnt[s_] - b_);
+        const float* src = A.rec + ((size_t)seg * A.HW + b_) * kRecStride;
+        float* dst = RAW + buf * RAWF;
+        for (int i = tid; i < nb * (kRecStride / 4); i += kWT) cp_async16(dst + 4 * i, src + 4 * i);
+      }
+      cp_async_commit();
+    };
+    skip_empty(si, base);
+    issue(si, base, 0);
+    int buf = 0;
+    while (si < kWMaxSeg) {
+      const int nb = min(NB, s_cnt[si] - base);
+      int nsi = si, nbase = base + NB;
+      skip_empty(nsi, nbase);
+      issue(nsi, nbase, buf ^ 1);
+      cp_async_wait<1>();
+      __syncthreads();                                   // raw batch landed; previous batch's tiles fully consumed
+      // record-major raw -> feature-major tiles (zero padded to NB cells)
+      {
+        const float* raw = RAW + buf * RAWF;
+        for (int i = tid; i < NB * kRecStride; i += kWT) {
+          const int cl = i % NB, f = i / NB;
+          const float v = cl < nb ? raw[cl * kRecStride + f] : 0.f;
+          if (f < C3) Yt[f * NBP + cl] = v;
+          else if (f < kRecXs) GDt[(f - kRecU) * NBP + cl] = v;
+          else if (f < kRecTh) XSt[(f - kRecXs) * NBP + cl] = v;
+          else if (f < kRecAs) GMt[(f - kRecTh) * NBP + cl] = v;
+          else if (f == kRecAs) ASv[cl] = v;
+        }
       }
       __syncthreads();
-      // G1/G2: h = relu(W1 y + b1), gh = (W2^T gd) * [h > 0]
+      // G1/G2: h = relu(W1 y + b1), gh = (W2^T gd) * [h > 0]: one 4 cells x 4 units tile per thread
       {
-        constexpr int CG = NB / 4, JGn = kWT / CG;       // 16 cell groups x 16 hidden groups
-        const int cgp = tid % CG, jg0 = tid / CG;
-        for (int jt = jg0; jt * 4 < HID; jt += JGn) {
-          const int j = jt * 4;
-          float acc[4][4], g2[4][4];
-          const float4 bb = *reinterpret_cast<const float4*>(sb1 + j);
+        const int j = jt * 4;
+        float acc[4][4], g2[4][4];
+        const float4 bb = *reinterpret_cast<const float4*>(sb1 + j);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          acc[m][0] = bb.x; acc[m][1] = bb.y; acc[m][2] = bb.z; acc[m][3] = bb.w;
+          g2[m][0] = g2[m][1] = g2[m][2] = g2[m][3] = 0.f;
+        }
+#pragma unroll 8
+        for (int kk = 0; kk < C3; ++kk) {
+          const float4 yv = *reinterpret_cast<const float4*>(Yt + kk * NBP + 4 * cgp);
+          const float4 w = *reinterpret_cast<const float4*>(sW1T + kk * HID + j);
+          const float ym[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
-            acc[m][0] = bb.x; acc[m][1] = bb.y; acc[m][2] = bb.z; acc[m][3] = bb.w;
-            g2[m][0] = g2[m][1] = g2[m][2] = g2[m][3] = 0.f;
+            acc[m][0] = fmaf(ym[m], w.x, acc[m][0]); acc[m][1] = fmaf(ym[m], w.y, acc[m][1]);
+            acc[m][2] = fmaf(ym[m], w.z, acc[m][2]); acc[m][3] = fmaf(ym[m], w.w, acc[m][3]);
           }
-#pragma unroll 4
-          for (int kk = 0; kk < C3; ++kk) {
-            const float4 yv = *reinterpret_cast<const float4*>(Yt + kk * NBP + 4 * cgp);
-            const float4 w = *reinterpret_cast<const float4*>(sW1T + kk * HID + j);
-            const float ym[4] = {yv.x, yv.y, yv.z, yv.w};
+        }
+#pragma unroll 8
+        for (int cc = 0; cc < C; ++cc) {
+          const float4 gv = *reinterpret_cast<const float4*>(GDt + cc * NBP + 4 * cgp);
+          const float4 w = *reinterpret_cast<const float4*>(sW2 + cc * HID + j);
+          const float gm[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              acc[m][0] = fmaf(ym[m], w.x, acc[m][0]); acc[m][1] = fmaf(ym[m], w.y, acc[m][1]);
-              acc[m][2] = fmaf(ym[m], w.z, acc[m][2]); acc[m][3] = fmaf(ym[m], w.w, acc[m][3]);
-            }
+          for (int m = 0; m < 4; ++m) {
+            g2[m][0] = fmaf(gm[m], w.x, g2[m][0]); g2[m][1] = fmaf(gm[m], w.y, g2[m][1]);
+            g2[m][2] = fmaf(gm[m], w.z, g2[m][2]); g2[m][3] = fmaf(gm[m], w.w, g2[m][3]);
           }
-#pragma unroll 4
-          for (int cc = 0; cc < C; ++cc) {
-            const float4 gv = *reinterpret_cast<const float4*>(GDt + cc * NBP + 4 * cgp);
-            const float4 w = *reinterpret_cast<const float4*>(sW2 + cc * HID + j);
-            const float gm[4] = {gv.x, gv.y, gv.z, gv.w};
+        }
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              g2[m][0] = fmaf(gm[m], w.x, g2[m][0]); g2[m][1] = fmaf(gm[m], w.y, g2[m][1]);
-              g2[m][2] = fmaf(gm[m], w.z, g2[m][2]); g2[m][3] = fmaf(gm[m], w.w, g2[m][3]);
-            }
-          }
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            float4 hv, gv;
-            hv.x = fmaxf(acc[0][jj], 0.f); hv.y = fmaxf(acc[1][jj], 0.f);
-            hv.z = fmaxf(acc[2][jj], 0.f); hv.w = fmaxf(acc[3][jj], 0.f);
-            gv.x = acc[0][jj] > 0.f ? g2[0][jj] : 0.f; gv.y = acc[1][jj] > 0.f ? g2[1][jj] : 0.f;
-            gv.z = acc[2][jj] > 0.f ? g2[2][jj] : 0.f; gv.w = acc[3][jj] > 0.f ? g2[3][jj] : 0.f;
-            *reinterpret_cast<float4*>(Ht + (j + jj) * NBP + 4 * cgp) = hv;
-            *reinterpret_cast<float4*>(GHt + (j + jj) * NBP + 4 * cgp) = gv;
-          }
+        for (int jj = 0; jj < 4; ++jj) {
+          float4 hv, gv;
+          hv.x = fmaxf(acc[0][jj], 0.f); hv.y = fmaxf(acc[1][jj], 0.f);
+          hv.z = fmaxf(acc[2][jj], 0.f); hv.w = fmaxf(acc[3][jj], 0.f);
+          gv.x = acc[0][jj] > 0.f ? g2[0][jj] : 0.f; gv.y = acc[1][jj] > 0.f ? g2[1][jj] : 0.f;
+          gv.z = acc[2][jj] > 0.f ? g2[2][jj] : 0.f; gv.w = acc[3][jj] > 0.f ? g2[3][jj] : 0.f;
+          *reinterpret_cast<float4*>(Ht + (j + jj) * NBP + 4 * cgp) = hv;
+          *reinterpret_cast<float4*>(GHt + (j + jj) * NBP + 4 * cgp) = gv;
         }
       }
       __syncthreads();
       // dW1 += GH^T Y, db1 += colsum(GH)   (padding cells have gd = 0 -> gh = 0)
+#pragma unroll 2
       for (int c4 = 0; c4 < NB / 4; ++c4) {
         float4 g[4];
 #pragma unroll
@@ -643,6 +676,7 @@ __global__ void __launch_bounds__(kWT) k_rep_wgrad(WgradArgs A, Packed P, const 
         }
       }
       // dW2 += GD^T H
+#pragma unroll 2
       for (int c4 = 0; c4 < NB / 4; ++c4) {
         float4 hh[4];
 #pragma unroll
@@ -656,6 +690,7 @@ __global__ void __launch_bounds__(kWT) k_rep_wgrad(WgradArgs A, Packed P, const 
       }
       // dWm += GM^T XS, dbm += GM . AS   (graph_augmentation.py:57 msg_proj)
       if (graph) {
+#pragma unroll
         for (int c4 = 0; c4 < NB / 4; ++c4) {
           const float4 gmv = *reinterpret_cast<const float4*>(GMt + mc * NBP + 4 * c4);
           const float4 xv = *reinterpret_cast<const float4*>(XSt + mci * NBP + 4 * c4);
@@ -663,7 +698,9 @@ __global__ void __launch_bounds__(kWT) k_rep_wgrad(WgradArgs A, Packed P, const 
           if (mci == 0) abm += dot4f(gmv, *reinterpret_cast<const float4*>(ASv + 4 * c4));
         }
       }
+      si = nsi; base = nbase; buf ^= 1;
     }
+    cp_async_wait<0>();
   }
   // one partial per block (canonical layout); the block's row was zeroed by the launcher
   float* wp = A.wpart + (size_t)blockIdx.x * A.wtotal;
@@ -827,8 +864,8 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
   int nblk = nseg < kMaxWgradBlocks ? nseg : kMaxWgradBlocks;
   if (nblk < 1) nblk = 1;
   GNCA_CHECK_CUDA(cudaMemsetAsync(wpart, 0, (size_t)nblk * L.total * sizeof(float), st));
-  const size_t wsmem = ((size_t)3 * C * 128 + 128 + (size_t)C * 128 + (size_t)(3 * C + 3 * C) * kWNBP + kWNBP +
-                        2 * (size_t)128 * kWNBP) * sizeof(float);
+  const size_t wsmem = ((size_t)3 * C * 128 + 128 + (size_t)C * 128 + 2 * (size_t)kWNB * kRecStride +
+                        (size_t)(3 * C + 3 * C) * kWNBP + kWNBP + 2 * (size_t)128 * kWNBP) * sizeof(float);
   GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_wgrad<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
   prof_begin(PROF_BWD_MLP, st);
   k_rep_wgrad<16><<<nblk, kWT, wsmem, st>>>(A, P, packed);
