@@ -8,15 +8,16 @@
 //               is only the propagation of g = dL/dx_t; per step:
 //                 A0  inactive cells of my band: per-channel sums of the gated gradient (their tanh' is a per-channel
 //                     constant) -> their share of the GroupNorm-backward sums S1, S2, dgamma, dbeta
-//                 A   my share of the ACTIVE cells (balanced over the cluster like the forward): gz = g * eta * tanh'
+//                 A   active cells of my band: gz = g * eta * tanh' -> L2 scratch (by slot)
 //                 --  S1, S2 partials -> every CTA of the cluster (DSMEM)                        [cluster barrier 1]
-//                 B   warp-autonomous tiles: gd = dL/du, hidden layer recomputed from y in registers, gh, gy = W1^T gh as
+//                 B   my SHARE of the active cells (balanced over the cluster like the forward), warp-autonomous tiles:
+//                     gd = dL/du, hidden layer recomputed from y in registers, gh, gy = W1^T gh as
 //                     three 16-channel shuffle reduce-scatters, message backward; gd / gm go back into the record, gy and
 //                     g_xs of the cell into an L2-resident per-cell scratch                       [cluster barrier 2]
 //                 C   my band of cells: g_t = gated g_{t+1} + perception transpose (gather from active neighbours) +
-//                     message transpose (gather from active receivers at +offset)                  [cluster barrier 3]
-//               g lives in L2 (cell-major ping-pong, 100 KB per sample) because an active cell may be handled by any CTA
-//               of the cluster; my band of it is also kept in shared memory.
+//                     message transpose (gather from active receivers at +offset), in place in shared memory
+//               g itself never leaves shared memory (each CTA owns a band of it for the whole sweep); only gz of the
+//               active cells and their gy / g_xs travel through L2 between the CTAs of the cluster.
 //   k_rep_wgrad weight gradients have no sequential dependence: one fully parallel pass over ALL records of the rollout
 //               (batches of 64 cells through the small GEMMs as FFMA register tiles, accumulators in registers for the
 //               whole kernel, one partial per block, no atomics) -> k_rep_wreduce sums the partials in a fixed order.
@@ -38,16 +39,15 @@ constexpr int kQG = 4;            // cells per tile
 
 struct RepBwdArgs {
   StepArgs s;
-  int T, NC, ucap, over_cap;
+  int T, NC;
   float inv_n;
   float* rec;
   const uint32_t* masks;
   const float* stats;         // [T][B][2]
   const float* gT;            // [B][C][HW]
   float* g0;                  // [B][C][HW]
-  float* Gbuf;                // [2][B][HW][C] cell-major ping-pong of g (L2)
+  float* GZ;                  // [B][HW][C] gz of the active cells of the current step, by slot (L2)
   float* RG;                  // [B][HW][64]   gy (48) | g_xs (16) of the active cells of the current step (L2)
-  float* over;                // [B*NC][over_cap][C] overflow of the in-smem gz buffer
   float* affpart;             // [B*NC][2C] dgamma | dbeta partials
   const float* damage;
   int damage_step;
@@ -85,10 +85,10 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   const int band_lo = (HW * rank) >> lnc, band_hi = (HW * (rank + 1)) >> lnc, nband = band_hi - band_lo;
   const int bandcap = ((HW + NC - 1) / NC) + 1;
   float* sG = sW2P + HID * kQW2S;                             // [bandcap][C] my band of g (cell-major)
-  float* sGZ = sG + (size_t)bandcap * C;                      // [ucap][C] gz of my active cells
-  float* sY = sGZ + (size_t)R.ucap * C;                       // [kQW][3C][G]
+  float* sY = sG + (size_t)bandcap * C;                       // [kQW][3C][G]
   float* sGD = sY + kQW * C3 * G;                             // [kQW][C][G]
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(sGD + kQW * C * G);   // [bandcap] cell index of my active cells
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(sGD + kQW * C * G);   // [bandcap] my SHARE of the active cells
+  unsigned short* s_blist = s_list + ((bandcap + 7) & ~7);                          // [bandcap] active cells of my BAND
 
   __shared__ uint32_t s_bAS[kMaskWords], s_bAct[kMaskWords], s_bPost[kMaskWords];
   __shared__ __align__(16) int s_wtot[kQW];
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   __shared__ float s_sums[2];
   __shared__ signed char s_off[2 * 16];
   __shared__ float s_gain;
+  __shared__ int s_bandbase[2];            // slot of the first active cell at / after band_lo, band_hi
 
 #pragma unroll 1
   for (int i = tid; i < C3 * HID; i += kQT) {
@@ -115,11 +116,10 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   const float gam_c = gn ? packed[P.gamma + c] : 1.f, bet_c = gn ? packed[P.beta + c] : 0.f;
 
   const size_t sample_off = (size_t)b * C * HW;
-  float* Gs[2] = {R.Gbuf + ((size_t)0 * a.B + b) * HW * C, R.Gbuf + ((size_t)1 * a.B + b) * HW * C};
+  float* GZs = R.GZ + (size_t)b * HW * C;
   float* RGs = R.RG + (size_t)b * HW * 64;
-  float* over = R.over ? R.over + (size_t)blockIdx.x * R.over_cap * C : nullptr;
 
-  // g_T (NCHW) -> my band in smem + cell-major global copy
+  // g_T (NCHW) -> my band in smem (g never leaves shared memory: the band owner gates it and gathers into it)
   {
     const int n8 = (nband + 7) & ~7;
 #pragma unroll 1
@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       if (cl < nband) {
         const float v = R.gT[sample_off + (size_t)ch * HW + band_lo + cl];
         sG[cl * C + ch] = v;
-        Gs[0][(size_t)(band_lo + cl) * C + ch] = v;
       }
     }
   }
@@ -145,7 +144,6 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   float* myY = sY + warp * (C3 * G);
   float* myGD = sGD + warp * (C * G);
   float dgam = 0.f, dbet = 0.f;              // this lane's channel c, summed over its cells / steps
-  int cur = 0;
 
   for (int t = R.T - 1; t >= 0; --t) {
     const bool dmg = R.damage && t == R.damage_step;
@@ -155,12 +153,9 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
 #pragma unroll 1
         for (int i = tid; i < nband * C; i += kQT) {
           const int cl = i / C, ch = i - cl * C;
-          const float v = sG[i] * D[(size_t)ch * HW + band_lo + cl];
-          sG[i] = v;
-          Gs[cur][(size_t)(band_lo + cl) * C + ch] = v;
+          sG[i] *= D[(size_t)ch * HW + band_lo + cl];
         }
         __syncthreads();
-        cl_sync_all();
       }
       continue;
     }
@@ -210,17 +205,25 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       nact = tot;
       const int lo = (tot * rank) >> lnc, hi = (tot * (rank + 1)) >> lnc;
       n_my = hi - lo; lo_my = lo;
+      const int slot_q = base + pre + __popc(wd & ((1u << qsh) - 1u));      // slot of the first active cell of my quad
+      if (qv && qcell == band_lo) s_bandbase[0] = slot_q;                   // band_lo, band_hi are multiples of 4
+      if (qv && qcell == band_hi) s_bandbase[1] = slot_q;
+      if (tid == 0 && band_hi == HW) s_bandbase[1] = tot;
+      __syncthreads();
       if (nib) {
-        int slot = base + pre + __popc(wd & ((1u << qsh) - 1u));
+        int slot = slot_q;
+        const int bb = s_bandbase[0];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (nib & (1u << j)) {
             if (slot >= lo && slot < hi) s_list[slot - lo] = (unsigned short)(qcell + j);
+            if (qcell >= band_lo && qcell < band_hi) s_blist[slot - bb] = (unsigned short)(qcell + j);
             ++slot;
           }
         }
       }
     }
+    const int bandbase = s_bandbase[0], n_band = s_bandbase[1] - s_bandbase[0];
     // ---- A0: inactive cells of my band: per-channel sums of the gated gradient --------------------------------------
     float s1 = 0.f, s2 = 0.f;
     {
@@ -247,20 +250,19 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         dgam += gzs * uh0; dbet += gzs;
       }
     }
-    // ---- A: my active cells: gz = gated g * eta * (1 - tanh^2(gn(u)))  (ncagraph.py:153-166 backward) -------------
+    // ---- A: active cells of my BAND (g is resident here): gz = gated g * eta * (1 - tanh^2(gn(u)))  -> GZ[slot] in L2
+    //         (ncagraph.py:153-166 backward); the heavy part (B) is done by whichever CTA the balanced split picks
     const float sc_c = s_aff[0][c], bi_c = s_aff[1][c];
-    const float* gin = Gs[cur];
     const size_t rec_base = ((size_t)t * a.B + b) * HW;
-#pragma unroll 1
-    for (int sl = warp * CPL + hwi; sl < n_my; sl += kQW * CPL) {
-      const int cell = s_list[sl];
-      float g = __ldcg(gin + (size_t)cell * C + c);
+#pragma unroll 2
+    for (int bi_ = warp * CPL + hwi; bi_ < n_band; bi_ += kQW * CPL) {
+      const int cell = s_blist[bi_];
+      float g = sG[(cell - band_lo) * C + c];
       if (c == 3 && !((s_bPost[cell >> 5] >> (cell & 31)) & 1u)) g = 0.f;
-      const float u = __ldcg(R.rec + (rec_base + lo_my + sl) * kRecStride + kRecU + c);
+      const float u = __ldcg(R.rec + (rec_base + bandbase + bi_) * kRecStride + kRecU + c);
       const float th = tanhf(fmaf(u, sc_c, bi_c));
       const float gz = g * eta * (1.f - th * th);
-      float* dst = sl < R.ucap ? sGZ + sl * C + c : over + (size_t)(sl - R.ucap) * C + c;
-      *dst = gz;
+      GZs[(size_t)(bandbase + bi_) * C + c] = gz;
       if (gn) {
         const float uh = (u - mu) * rstd, gu = gz * gam_c;
         s1 += gu; s2 = fmaf(gu, uh, s2);
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         dst[rank * 2] = t1; dst[rank * 2 + 1] = t2;
       }
     }
-    cl_sync_all();                                                            // ---- cluster barrier 1
+    cl_sync_all();                                                            // ---- cluster barrier 1: S1/S2 partials, GZ visible
     float s1n = 0.f, s2n = 0.f;
     if (gn) {
       for (int r = 0; r < NC; ++r) { s1n += s_parts[r][0]; s2n += s_parts[r][1]; }
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         myY[c * G + m] = __ldcg(rc + c);
         myY[(C + c) * G + m] = __ldcg(rc + C + c);
         myY[(2 * C + c) * G + m] = __ldcg(rc + 2 * C + c);
-        const float gz = slc < R.ucap ? sGZ[slc * C + c] : over[(size_t)(slc - R.ucap) * C + c];
+        const float gz = __ldcg(GZs + (size_t)(lo_my + slc) * C + c);
         float gd = gz;
         if (gn) {
           const float uh = (__ldcg(rc + kRecU + c) - mu) * rstd;
@@ -409,7 +411,6 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
     cl_sync_all();                                                            // ---- cluster barrier 2: RG visible
     // ---- C: my band: g_t = gated g_{t+1} + perception^T (gy of active neighbours) + message^T (g_xs of receivers) --
     {
-      float* gout = Gs[cur ^ 1];
       const float wuni = k > 0 ? 1.0f / (float)k : 0.f;
       auto actbit = [&](int cell) -> bool { return (s_bAct[cell >> 5] >> (cell & 31)) & 1u; };
 #pragma unroll 1
@@ -460,11 +461,9 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
           g.z *= D[(size_t)(4 * cq + 2) * HW]; g.w *= D[(size_t)(4 * cq + 3) * HW];
         }
         *reinterpret_cast<float4*>(sG + cl * C + 4 * cq) = g;
-        *reinterpret_cast<float4*>(gout + (size_t)cell * C + 4 * cq) = g;
       }
     }
-    cl_sync_all();                                                            // ---- cluster barrier 3: g_t visible
-    cur ^= 1;
+    __syncthreads();
     (void)nact;
   }
 
@@ -734,11 +733,10 @@ __global__ void k_rep_wreduce(int nblk, int64_t total, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-static size_t rep_bwd_smem_bytes(int C, int HW, int NC, int ucap) {
+static size_t rep_bwd_smem_bytes(int C, int HW, int NC) {
   const int bandcap = ((HW + NC - 1) / NC) + 1;
-  size_t f = (size_t)3 * C * 128 + 128 + 128 * kQW2S + (size_t)bandcap * C + (size_t)ucap * C + (size_t)kQW * 3 * C * kQG +
-             (size_t)kQW * C * kQG;
-  return f * sizeof(float) + (size_t)((bandcap + 7) & ~7) * sizeof(unsigned short) + 32;
+  size_t f = (size_t)3 * C * 128 + 128 + 128 * kQW2S + (size_t)bandcap * C + (size_t)kQW * 3 * C * kQG + (size_t)kQW * C * kQG;
+  return f * sizeof(float) + 2 * (size_t)((bandcap + 7) & ~7) * sizeof(unsigned short) + 32;
 }
 
 size_t rep_bptt_bytes(const gnca_model& m, int B, int H, int W, int T) {
@@ -764,7 +762,7 @@ void rep_bptt_carve(void* base, int B, int H, int W, int T, float** rec, uint32_
 
 size_t rep_bwd_workspace_bytes(const gnca_model& m, int B, int H, int W) {
   const size_t HW = (size_t)H * W, C = m.C;
-  size_t f = 2 * (size_t)B * HW * C + (size_t)B * HW * 64 + (size_t)B * HW * C /*over*/ + (size_t)B * 8 * 2 * C;
+  size_t f = (size_t)B * HW * C /*GZ*/ + (size_t)B * HW * 64 /*RG*/ + (size_t)B * 8 * 2 * C;
   const gnca_layout L = make_layout(m);
   f += (size_t)kMaxWgradBlocks * (size_t)L.total;
   return f * sizeof(float) + 1024;
@@ -784,9 +782,8 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
   rep_bptt_carve(bptt, B, H, W, sched.T, &rec, &masks, &stats);
   const gnca_layout L = make_layout(m);
   float* ws = reinterpret_cast<float*>(workspace);
-  float* Gbuf = ws; ws += 2 * (size_t)B * HW * C;
+  float* GZ = ws; ws += (size_t)B * HW * C;
   float* RG = ws; ws += (size_t)B * HW * 64;
-  float* over = ws; ws += (size_t)B * HW * C;
   float* affpart = ws; ws += (size_t)B * 8 * 2 * C;
   float* wpart = ws;
 
@@ -798,22 +795,20 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
   R.s.steps = sched.steps;
   R.T = sched.T;
   R.inv_n = (float)(1.0 / ((double)C * (double)H * (double)W));
-  R.rec = rec; R.masks = masks; R.stats = stats; R.gT = gT; R.g0 = g0; R.Gbuf = Gbuf; R.RG = RG; R.over = over;
+  R.rec = rec; R.masks = masks; R.stats = stats; R.gT = gT; R.g0 = g0; R.GZ = GZ; R.RG = RG;
   R.affpart = affpart;
   R.damage = sched.damage; R.damage_step = sched.damage_step;
 
   const char* env_nc = getenv("GNCA_RESIDENT_NC");
   const int cands[4] = {8, 4, 2, 1};
-  int pick = -1, pick_ucap = 0;
+  int pick = -1;
   size_t pick_smem = 0;
   for (int pass = 0; pass < 2 && pick < 0; ++pass) {
     for (int ci = (pass == 0 ? 0 : 3); ci >= 0 && ci < 4; ci += (pass == 0 ? 1 : -1)) {
       const int NC = cands[ci];
       if (env_nc && atoi(env_nc) != NC) continue;
-      const int share = (HW + NC - 1) / NC + 1;
-      int ucap = share < 512 ? share : 512;
-      size_t smem = rep_bwd_smem_bytes(C, HW, NC, ucap);
-      while (smem > 226 * 1024 && ucap > 128) { ucap -= 64; smem = rep_bwd_smem_bytes(C, HW, NC, ucap); }
+      if ((HW % (4 * NC)) != 0) continue;                 // bands start at a quad boundary
+      const size_t smem = rep_bwd_smem_bytes(C, HW, NC);
       if (smem > 226 * 1024) continue;
       GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cudaLaunchConfig_t q{};
@@ -828,18 +823,13 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
         continue;
       }
       if (pass == 0 && B > ncl && !env_nc) continue;
-      pick = NC; pick_ucap = ucap; pick_smem = smem;
+      pick = NC; pick_smem = smem;
       break;
     }
   }
   if (pick < 0) return GNCA_ERR_UNSUPPORTED;
-  R.NC = pick; R.ucap = pick_ucap;
-  {
-    const int share = (HW + pick - 1) / pick + 1;
-    R.over_cap = share > pick_ucap ? share - pick_ucap : 0;
-  }
-  if (getenv("GNCA_DEBUG"))
-    fprintf(stderr, "[gnca] resident bwd: B=%d NC=%d ucap=%d over=%d smem=%zu\n", B, pick, R.ucap, R.over_cap, pick_smem);
+  R.NC = pick;
+  if (getenv("GNCA_DEBUG")) fprintf(stderr, "[gnca] resident bwd: B=%d NC=%d smem=%zu\n", B, pick, pick_smem);
   GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pick_smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(B * pick);
