@@ -37,6 +37,8 @@ FLOP_FWD_GRAPH_S = 17.9e3
 FLOP_FWDBWD_GRAPH_S = 53.6e3
 FLOP_FWD_GRAPH_L = 36.7e3
 FP32_LANES = 148 * 128 * 2           # FMA lanes x 2 flop
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_DRAM_BYTES = {("c2", "k_rep_fwd"): 1112832}
 
 
 def load_weights(name):
@@ -173,39 +175,9 @@ def run_reference_arm(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2")
-    ap.add_argument("--rollout-impl", default="auto", choices=["auto", "streaming", "resident", "banded"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--T", type=int, default=0, help="development: override the number of CA steps per rollout")
-    ap.add_argument("--B", type=int, default=0, help="development: override the per-GPU batch")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    cfg = workload_cfg(args.workload)
-    if args.T > 0:
-        cfg["T"] = args.T
-    if args.B > 0:
-        cfg["B"] = args.B
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
-    if args.impl == "reference":
-        run_reference_arm(args, cfg, rank)
-        return
-
+def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_roofline=True):
+    """Times one workload: returns dict(value, ms_per_step, e2e, launches, roofline, clocks, data)."""
     import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
     import graph_neural_cellular_automata_b200 as G
     from graph_neural_cellular_automata_b200 import _lib
     from graph_neural_cellular_automata_b200.rollout import make_schedule, rollout
@@ -273,9 +245,9 @@ def main():
                              fire="philox", seed=seed)
 
     # ---------------- device-resident timing (value) ----------------
-    scheds = [new_schedule(1000 + i) for i in range(args.warmup + args.steps)]
+    scheds = [new_schedule(1000 + i) for i in range(warmup + steps)]
     torch.cuda.synchronize()
-    for i in range(args.warmup):
+    for i in range(warmup):
         one_rollout(x0_dev, scheds[i])
     torch.cuda.synchronize()
     if world > 1:
@@ -285,11 +257,11 @@ def main():
     launches0 = lib.gnca_launch_count()
     evs = []
     torch.cuda.synchronize()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.fill_(float(i))                        # L2 flush between timed iterations (outside the events)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        one_rollout(x0_dev, scheds[args.warmup + i])
+        one_rollout(x0_dev, scheds[warmup + i])
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()
@@ -303,7 +275,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
-    value = world * updates * args.steps / (dev_ms_max * 1e-3)
+    value = world * updates * steps / (dev_ms_max * 1e-3)
 
     # ---------------- end-to-end through the public API with host buffers ----------------
     def e2e_once(seed):
@@ -319,29 +291,29 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         e2e_once(6000 + i)
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * updates * args.steps / float(t.item())
+    e2e_value = world * updates * steps / float(t.item())
     sched_bytes = T * 4 * 2 + T * 8 * 2
     e2e = {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": int(x0_host.numel() * 4 + sched_bytes),
-           "d2h_bytes_per_step": int(xT_host.numel() * 4), "ms_per_step": float(t.item()) / args.steps * 1e3}
+           "d2h_bytes_per_step": int(xT_host.numel() * 4), "ms_per_step": float(t.item()) / steps * 1e3}
 
     # ---------------- roofline of the dominant kernel (library event hook), rank 0 ----------------
     roof = None
-    if rank == 0:
+    if rank == 0 and with_roofline:
         lib.gnca_profile_enable(1)
-        nprof = min(args.steps, 5)
+        nprof = min(steps, 5)
         for i in range(nprof):
             flush.fill_(1.0)
-            one_rollout(x0_dev, scheds[args.warmup + i])
+            one_rollout(x0_dev, scheds[warmup + i])
         torch.cuda.synchronize()
         lib.gnca_profile_enable(0)
         per_kernel = {}
-        for kid, kname in ((0, "k_update"), (1, "k_apply"), (2, "k_resident_fwd"), (3, "k_bwd_mlp / k_rep_wgrad"), (6, "k_resident_bwd")):
+        for kid, kname in ((0, "k_update"), (1, "k_apply"), (2, "k_rep_fwd"), (3, "k_rep_wgrad"), (6, "k_rep_bwd")):
             ms, n = ctypes.c_double(0), ctypes.c_ulonglong(0)
             lib.gnca_profile_read(kid, ctypes.byref(ms), ctypes.byref(n))
             if n.value:
@@ -357,7 +329,7 @@ def main():
             peak = FP32_LANES * mhz * 1e6 / 1e12
             achieved = flops_per_launch / avg_s / 1e12
             roof = {"bound": "fp32_fma", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "avg_launch_ms": avg_s * 1e3, "launches_per_step": n / nprof,
+                    "frac": achieved / peak, "traffic": NCU_DRAM_BYTES.get((cfg["name"][:2], kname)), "avg_launch_ms": avg_s * 1e3, "launches_per_step": n / nprof,
                     "peak_source": f"derived: 148 SM x 128 FMA lanes x 2 x {mhz} MHz (MEASURED_PEAKS.json has no fp32 entry; "
                                    "hbm_gbs 6547.8 measured is far from binding: see hbm_view)",
                     "note": "achieved = DENSE algorithmic flops (every cell counted) / measured kernel time; the kernel "
@@ -365,7 +337,61 @@ def main():
                     "hbm_view": {"algorithmic_bytes_per_step": int(2 * x0_host.numel() * 4),
                                  "achieved_GBps": 2 * x0_host.numel() * 4 * nprof / (ms * 1e-3) / 1e9,
                                  "peak_GBps": 6547.8},
-                    "share_of_step": ms / nprof / (dev_ms_max / args.steps), "kernels": kernels_ms}
+                    "share_of_step": ms / nprof / (dev_ms_max / steps), "kernels": kernels_ms}
+
+    return {"value": value, "ms_per_step": dev_ms_max / steps, "e2e": e2e, "launches": int(launches), "roofline": roof,
+            "clocks": sampler.result(), "data": data, "dims": (C_, H, W, B, T)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--rollout-impl", default="auto", choices=["auto", "streaming", "resident", "banded"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-extra", action="store_true", help="skip the fwd+bwd (c3) measurement of the default run")
+    ap.add_argument("--T", type=int, default=0, help="development: override the number of CA steps per rollout")
+    ap.add_argument("--B", type=int, default=0, help="development: override the per-GPU batch")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = workload_cfg(args.workload)
+    if args.T > 0:
+        cfg["T"] = args.T
+    if args.B > 0:
+        cfg["B"] = args.B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    res = run_workload(cfg, args, world, rank, local_rank, dev, args.steps, args.warmup)
+    C_, H, W, B, T = res["dims"]
+    value, e2e, launches, roof, data = res["value"], res["e2e"], res["launches"], res["roofline"], res["data"]
+
+    # the other half of the metric ("fwd, fwd+bwd"): the training hot path (fwd with BPTT records, loss, resident
+    # backward, batched weight gradients, all-reduce, normalise + Adam) on BASELINE configs[2]'s shape, short regime
+    train = None
+    if args.workload == "c2" and not args.no_train_extra:
+        cfg3 = workload_cfg("c3")
+        r3 = run_workload(cfg3, args, world, rank, local_rank, dev, max(3, min(args.steps, 10)), 3, with_roofline=True)
+        train = {"metric": "graph-NCA cell-updates/s (fwd+bwd)", "value": r3["value"], "unit": "cell-updates/s",
+                 "ms_per_step": r3["ms_per_step"], "e2e": r3["e2e"], "gpu_launches": r3["launches"],
+                 "config": {"workload": cfg3["name"], "B_per_gpu": cfg3["B"], "T": cfg3["T"], "fire_rate": cfg3["fire_rate"],
+                            "message_every": cfg3["message_every"]},
+                 "kernels": (r3["roofline"] or {}).get("kernels")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not cfg["train"]:
@@ -374,14 +400,14 @@ def main():
     if rank == 0:
         line = {"metric": "graph-NCA cell-updates/s (%s)" % ("fwd+bwd" if cfg["train"] else "fwd"), "value": value,
                 "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": data,
                 "config": {"workload": cfg["name"], "B_per_gpu": B, "T": T, "grid": [H, W], "channels": C_,
                            "hidden": cfg["hidden"], "fire_rate": cfg["fire_rate"], "offsets_per_step": 8,
                            "graph_shift": "torus", "fire_rng": "in-kernel philox", "rollout_impl": args.rollout_impl,
                            "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": f"dp{world} batch-sharded, no collective"},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof,
-                "cpu_baseline": cpu}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": res["clocks"], "roofline": roof,
+                "cpu_baseline": cpu, "fwd_bwd": train}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

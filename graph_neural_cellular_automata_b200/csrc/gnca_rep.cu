@@ -125,6 +125,10 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
   const int lnc = NC == 8 ? 3 : NC == 4 ? 2 : NC == 2 ? 1 : 0;
   const float thr = a.alpha_thr, gthr = a.graph_alpha_thr;
   const bool fast_alive = (thr >= 0.f) && (gthr == thr);
+  // From step 1 on, a cell that is not post-alive has alpha == 0 exactly (the gate), an inactive cell moves by at most
+  // update_gain, and only alive cells are active: with update_gain <= alpha_thr a cell outside dilate(alive(t)) cannot be
+  // alive at t+1, so its fire bit is never read and its Philox draw can be skipped.
+  const bool sparse_fire = fast_alive && a.update_gain <= thr && a.update_gain >= 0.f;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sW1T = reinterpret_cast<float*>(smem_raw);           // [3C][HID] hidden index permuted: lane l owns 4l..4l+3
@@ -215,7 +219,20 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     if (tid >= 32 && tid < 32 + 2 * k) s_off[buf][tid - 32] = nx_off;
   };
   // fire bits of 32 consecutive quads of step tn (fire_rate in s_fr[buf]) -> s_bFire[buf]  (ncagraph.py:144-146: u <= fr)
-  auto fire_task = [&](int task, int tn, int buf) {
+  // `sparse`: the caller guarantees that a cell outside the 3x3 dilation of the CURRENT alive bitmap cannot be alive at
+  // step tn (see sparse_fire below); a task none of whose cells is near an alive cell just writes zero words.
+  auto fire_task = [&](int task, int tn, int buf, bool sparse) {
+    if (sparse) {
+      const int c0 = task * 128 - W - 1, c1 = task * 128 + 127 + W + 1;          // cells whose alive bit can matter
+      const int w0 = max(c0, 0) >> 5, w1 = min(c1, HW - 1) >> 5;
+      uint32_t any = 0;
+      for (int w = w0 + lane; w <= w1; w += 32) any |= s_bAlive[w];
+      if (!__any_sync(0xffffffffu, any != 0)) {
+        const int q = task * 32 + lane;
+        if ((lane & 7) == 0) s_bFire[buf][q >> 3] = 0u;
+        return;
+      }
+    }
     const float frn = s_fr[buf];
     const int q = task * 32 + lane, qq = min(q, NQ - 1);     // every lane computes (clamped): no divergence before the shuffles
     uint32_t nib;
@@ -342,7 +359,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
   sched_commit(1);
   sched_fetch(2);
   __syncthreads();
-  if (R.T > 0) for (int task = warp; task < n_fire_tasks; task += kPW) fire_task(task, 0, 0);
+  if (R.T > 0) for (int task = warp; task < n_fire_tasks; task += kPW) fire_task(task, 0, 0, false);
   __syncthreads();
   prepare_from_state(0);
 
@@ -404,20 +421,17 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     // ---- S2: warp-autonomous tiles of G cells; then the side jobs of the step (fire bits of step t+1, BPTT
     //      history of x_t) handed out in chunks by a shared counter, so the warps without a tile take them ----------
     float ps1 = 0.f, ps2 = 0.f;
-    auto run_tiles = [&](auto gtag) {
+    auto run_tile = [&](auto gtag, const int slot0, const int lim) {      // cells [slot0, min(slot0 + G, lim)) of my list
       constexpr int G = decltype(gtag)::value;
       constexpr int MPL = G / CPL;                         // cells per lane
-      const int ntiles = (n_my + G - 1) / G;
-#pragma unroll 1
-      for (int tile = warp; tile < ntiles; tile += kPW) {
-        const int slot0 = tile * G;
+      {
         // 2a: sender table of the tile: (cell, offset) -> sender cell index or -1   (graph_augmentation.py:94-97,116-133)
         if (msg_on) {
           for (int p = lane; p < G * KP; p += 32) {
             const int m = p >> lkp, i = p & (KP - 1);
             short q = -1;
             if (i < k) {
-              const unsigned ent = s_list[min(slot0 + m, n_my - 1)];
+              const unsigned ent = s_list[min(slot0 + m, lim - 1)];
               int qy = (int)(ent >> 8) - (int)s_off[cur][2 * i], qx = (int)(ent & 255u) - (int)s_off[cur][2 * i + 1];
               qy += qy < 0 ? H : 0; qy -= qy >= H ? H : 0;
               qx += qx < 0 ? W : 0; qx -= qx >= W ? W : 0;
@@ -436,7 +450,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
 #pragma unroll
         for (int r = 0; r < MPL; ++r) {
           const int m = hwi + CPL * r;
-          const unsigned ent = s_list[min(slot0 + m, n_my - 1)];
+          const unsigned ent = s_list[min(slot0 + m, lim - 1)];
           const int y = (int)(ent >> 8), x = (int)(ent & 255u);
           const float* p = pb + (y * W + x) * st;
           const bool up = y > 0, dn = y < H - 1, lf = x > 0, rt = x < W - 1;
@@ -469,7 +483,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
             as = s_astab[nv];
           }
           xs[r] = xsv; asv[r] = as;
-          if (R.rec && slot0 + m < n_my) {          // forward half of the record (gnca_rep.h): y | u | xs | tanh(agg) | as
+          if (R.rec && slot0 + m < lim) {          // forward half of the record (gnca_rep.h): y | u | xs | tanh(agg) | as
             float* rc = R.rec + (((size_t)t * a.B + b) * HW + (size_t)(lo_my + slot0 + m)) * kRecStride;
             rc[c] = v_id; rc[C + c] = myY[(C + c) * G + m]; rc[2 * C + c] = myY[(2 * C + c) * G + m];
             rc[kRecXs + c] = xsv;
@@ -486,7 +500,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
             for (int ci = 0; ci < C; ++ci) agg = fmaf(wm[ci], __shfl_sync(0xffffffffu, xs[r], (lane & 16) | ci), agg);
             const float th = tanhf(agg);
             if (c >= c_lo) mval = th * gain_m;
-            if (R.rec && slot0 + hwi + CPL * r < n_my)
+            if (R.rec && slot0 + hwi + CPL * r < lim)
               R.rec[(((size_t)t * a.B + b) * HW + (size_t)(lo_my + slot0 + hwi + CPL * r)) * kRecStride + kRecTh + c] = th;
           }
           msg[r] = mval;
@@ -563,7 +577,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
           for (int e = 0; e < GB / 2; ++e) {
             const int r = (GB / 2) * blk + e, m = hwi + CPL * r;
             const int slot = slot0 + m;
-            if (slot < n_my) {
+            if (slot < lim) {
               const float u = pv[e] + msg[r];
               if (R.rec) R.rec[(((size_t)t * a.B + b) * HW + (size_t)(lo_my + slot)) * kRecStride + kRecU + c] = u;
               float* dst = slot < R.ucap ? sU + slot * C + c : over + (size_t)(slot - R.ucap) * C + c;
@@ -581,21 +595,39 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
       }
     };
     // tile size: as many warps as possible get a tile (latency), larger tiles amortise the weight reads (throughput)
-    const int Gt = n_my > 4 * kPW ? 8 : (n_my > 2 * kPW ? 4 : 2);
-    if (Gt == 8) run_tiles(std::integral_constant<int, 8>{});
-    else if (Gt == 4) run_tiles(std::integral_constant<int, 4>{});
-    else run_tiles(std::integral_constant<int, 2>{});
+    // Tile schedule.  Few cells (<= 64): tiles of 2 (<= 32 cells) or 4 handed out round-robin -- the phase is bound by
+    // shared-memory weight reads + instruction issue, fewer/larger tiles cost fewer instructions, and the warps without a
+    // tile do the side jobs meanwhile.  Many cells: every warp takes a contiguous, equally sized range and covers it with
+    // tiles of 8 / 4 / 2 cells, so all warps finish together (17 round-robin tiles of 8 would mean two full rounds).
+    static_assert(kPW == 16, "per-warp ranges");
+    if (n_my <= 64) {
+      if (n_my <= 32) {
+#pragma unroll 1
+        for (int s0 = 2 * warp; s0 < n_my; s0 += 2 * kPW) run_tile(std::integral_constant<int, 2>{}, s0, n_my);
+      } else {
+#pragma unroll 1
+        for (int s0 = 4 * warp; s0 < n_my; s0 += 4 * kPW) run_tile(std::integral_constant<int, 4>{}, s0, n_my);
+      }
+    } else {
+      const int w_lo = (n_my * warp) >> 4, w_hi = (n_my * (warp + 1)) >> 4;
+#pragma unroll 1
+      for (int s0 = w_lo; s0 < w_hi;) {
+        const int rem = w_hi - s0;
+        if (rem > 4) { run_tile(std::integral_constant<int, 8>{}, s0, w_hi); s0 += 8; }
+        else if (rem > 2) { run_tile(std::integral_constant<int, 4>{}, s0, w_hi); s0 += 4; }
+        else { run_tile(std::integral_constant<int, 2>{}, s0, w_hi); s0 += 2; }
+      }
+    }
     REP_MARK(9);
     {
       const int nf = (t + 1 < R.T) ? n_fire_tasks : 0, ntask = nf + n_hist_tasks;
       float* hdst = R.hist ? R.hist + (size_t)t * a.B * C * HW + sample_off : nullptr;
-      for (;;) {
-        int task = 0;
-        if (lane == 0) task = atomicAdd(&s_ctr, 1);
-        task = __shfl_sync(0xffffffffu, task, 0);
-        if (task >= ntask) break;
+      // static assignment (warps 15, 14, ... first: with few cells those have no tile); a shared work counter costs an
+      // atomic round trip per task on the critical path of whichever warp finishes its tiles first
+#pragma unroll 1
+      for (int task = kPW - 1 - warp; task < ntask; task += kPW) {
         if (task < nf) {
-          fire_task(task, t + 1, cur ^ 1);
+          fire_task(task, t + 1, cur ^ 1, sparse_fire && t >= 1);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -715,14 +747,9 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     {
       // my active cells: x + gain * tanh(gn(u)); written into every replica (alpha: pre-gate plane)
       const float sc = s_aff[0][c], bi = s_aff[1][c];
-      const int G = Gt;
-      const int ntiles = (n_my + G - 1) / G;
-      const int mpl = G / CPL;
 #pragma unroll 1
-      for (int tile = warp; tile < ntiles; tile += kPW) {
-        for (int r = 0; r < mpl; ++r) {
-          const int slot = tile * G + hwi + CPL * r;
-          if (slot >= n_my) continue;
+      for (int slot = warp * CPL + hwi; slot < n_my; slot += kPW * CPL) {
+        {
           const unsigned ent = s_list[slot];
           const int cell = (int)(ent >> 8) * W + (int)(ent & 255u);
           const float u = slot < R.ucap ? sU[slot * C + c] : over[(size_t)(slot - R.ucap) * C + c];

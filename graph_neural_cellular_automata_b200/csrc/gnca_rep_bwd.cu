@@ -36,6 +36,7 @@ constexpr int kQT = 512;          // threads per CTA (k_rep_bwd)
 constexpr int kQW = kQT / 32;
 constexpr int kQW2S = 20;         // padded row stride of W2^T
 constexpr int kQG = 4;            // cells per tile
+constexpr int kQW1S = 132;        // padded row stride of W1^T (floats): rows c, c+8 share banks only pairwise (2-way)
 
 struct RepBwdArgs {
   StepArgs s;
@@ -51,7 +52,18 @@ struct RepBwdArgs {
   float* affpart;             // [B*NC][2C] dgamma | dbeta partials
   const float* damage;
   int damage_step;
+  unsigned long long* dbg;    // optional phase-cycle counters (GNCA_PHASE_TIMING=<cta>)
+  int dbg_cta;
 };
+
+#define REPB_MARK(idx)                                                              \
+  do {                                                                              \
+    if (R.dbg && tid == 0) {                                                        \
+      const long long _n = clock64();                                               \
+      s_dbg[idx] += (unsigned long long)(_n - t_prev);                              \
+      t_prev = _n;                                                                  \
+    }                                                                               \
+  } while (0)
 
 __device__ __forceinline__ void cl_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -80,14 +92,15 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sW1T = reinterpret_cast<float*>(smem_raw);           // [3C][HID] permuted (lane l owns 4l..4l+3 <-> units l+32jj)
-  float* sb1 = sW1T + C3 * HID;
+  float* sb1 = sW1T + C3 * kQW1S;
   float* sW2P = sb1 + HID;                                    // [HID][kQW2S]
   const int band_lo = (HW * rank) >> lnc, band_hi = (HW * (rank + 1)) >> lnc, nband = band_hi - band_lo;
   const int bandcap = ((HW + NC - 1) / NC) + 1;
   float* sG = sW2P + HID * kQW2S;                             // [bandcap][C] my band of g (cell-major)
   float* sY = sG + (size_t)bandcap * C;                       // [kQW][3C][G]
   float* sGD = sY + kQW * C3 * G;                             // [kQW][C][G]
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(sGD + kQW * C * G);   // [bandcap] my SHARE of the active cells
+  float* sGH = sGD + kQW * C * G;                             // [kQW][G][HID] gh of the tile (permuted unit order)
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(sGH + kQW * G * HID);  // [bandcap] my SHARE of the active cells
   unsigned short* s_blist = s_list + ((bandcap + 7) & ~7);                          // [bandcap] active cells of my BAND
 
   __shared__ uint32_t s_bAS[kMaskWords], s_bAct[kMaskWords], s_bPost[kMaskWords];
@@ -100,12 +113,15 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   __shared__ signed char s_off[2 * 16];
   __shared__ float s_gain;
   __shared__ int s_bandbase[2];            // slot of the first active cell at / after band_lo, band_hi
+  __shared__ unsigned long long s_dbg[16];
+  if (threadIdx.x < 16) s_dbg[threadIdx.x] = 0;
+  long long t_prev = clock64();
 
 #pragma unroll 1
   for (int i = tid; i < C3 * HID; i += kQT) {
     const int kk = i / HID, jp = i - kk * HID;
     const int l = jp >> 2, jj = jp & 3;
-    sW1T[i] = packed[P.w1t + kk * HID + (l + 32 * jj)];
+    sW1T[kk * kQW1S + jp] = packed[P.w1t + kk * HID + (l + 32 * jj)];
   }
   if (tid < HID) { const int l = tid >> 2, jj = tid & 3; sb1[tid] = packed[P.b1 + l + 32 * jj]; }
 #pragma unroll 1
@@ -143,6 +159,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   const int qsh = 4 * (lane & 7), qword = min(q >> 3, kMaskWords - 1);
   float* myY = sY + warp * (C3 * G);
   float* myGD = sGD + warp * (C * G);
+  float* myGH = sGH + warp * (G * HID);
   float dgam = 0.f, dbet = 0.f;              // this lane's channel c, summed over its cells / steps
 
   for (int t = R.T - 1; t >= 0; --t) {
@@ -159,6 +176,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       }
       continue;
     }
+    REPB_MARK(0);
     // ---- masks, schedule, statistics of step t ----------------------------------------------------------------
     if (tid < NW) {
       const uint32_t* mk = R.masks + ((size_t)t * a.B + b) * 3 * kMaskWords;
@@ -224,6 +242,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       }
     }
     const int bandbase = s_bandbase[0], n_band = s_bandbase[1] - s_bandbase[0];
+    REPB_MARK(1);
     // ---- A0: inactive cells of my band: per-channel sums of the gated gradient --------------------------------------
     float s1 = 0.f, s2 = 0.f;
     {
@@ -250,6 +269,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         dgam += gzs * uh0; dbet += gzs;
       }
     }
+    REPB_MARK(2);
     // ---- A: active cells of my BAND (g is resident here): gz = gated g * eta * (1 - tanh^2(gn(u)))  -> GZ[slot] in L2
     //         (ncagraph.py:153-166 backward); the heavy part (B) is done by whichever CTA the balanced split picks
     const float sc_c = s_aff[0][c], bi_c = s_aff[1][c];
@@ -269,6 +289,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         dgam = fmaf(gz, uh, dgam); dbet += gz;
       }
     }
+    REPB_MARK(3);
     // ---- S1, S2: warp -> block -> every CTA of the cluster ---------------------------------------------------------
     {
       const float f1 = warp_sum(s1), f2 = warp_sum(s2);
@@ -283,7 +304,9 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         dst[rank * 2] = t1; dst[rank * 2 + 1] = t2;
       }
     }
+    REPB_MARK(4);
     cl_sync_all();                                                            // ---- cluster barrier 1: S1/S2 partials, GZ visible
+    REPB_MARK(5);
     float s1n = 0.f, s2n = 0.f;
     if (gn) {
       for (int r = 0; r < NC; ++r) { s1n += s_parts[r][0]; s2n += s_parts[r][1]; }
@@ -337,7 +360,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         for (int m = 0; m < G; ++m) { acc1[m][0] = bb.x; acc1[m][1] = bb.y; acc1[m][2] = bb.z; acc1[m][3] = bb.w; }
 #pragma unroll 8
         for (int kk = 0; kk < C3; ++kk) {
-          const float4 w = *reinterpret_cast<const float4*>(sW1T + kk * HID + 4 * lane);
+          const float4 w = *reinterpret_cast<const float4*>(sW1T + kk * kQW1S + 4 * lane);
           const float4 yv = *reinterpret_cast<const float4*>(myY + kk * G);
           const float ym[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
@@ -374,41 +397,47 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       for (int m = 0; m < G; ++m)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) gh[m][jj] = acc1[m][jj] > 0.f ? gh[m][jj] : 0.f;
-      // gy[kk][m] = sum_j W1[j][kk] gh[j][m]: per 16-channel block a shuffle reduce-scatter that leaves
-      // (cell hwi+2e, channel c) in this lane; block 0 = identity part, 1 = sobel_x part, 2 = sobel_y part
+      // gy[kk][m] = sum_j W1[j][kk] gh[j][m].  gh goes through the warp's shared-memory tile so that the lane that owns
+      // (cell hwi+2e, channel c) can run the three 128-long dot products itself (rows c, 16+c, 32+c of W1^T = identity /
+      // sobel_x / sobel_y parts): no cross-lane reduction.
 #pragma unroll
-      for (int kb = 0; kb < 3; ++kb) {
-        float pv[4 * C];
+      for (int m = 0; m < G; ++m)
+        *reinterpret_cast<float4*>(myGH + m * HID + 4 * lane) = make_float4(gh[m][0], gh[m][1], gh[m][2], gh[m][3]);
+      __syncwarp();
+      {
+        float gy[3][MPL];
 #pragma unroll
-        for (int kc = 0; kc < C; ++kc) {
-          const float4 w = *reinterpret_cast<const float4*>(sW1T + (kb * C + kc) * HID + 4 * lane);
+        for (int kb = 0; kb < 3; ++kb)
 #pragma unroll
-          for (int m = 0; m < G; ++m) {
-            const int idx = (m & 1) * (2 * C) + kc * 2 + (m >> 1);
-            pv[idx] = fmaf(w.x, gh[m][0], fmaf(w.y, gh[m][1], fmaf(w.z, gh[m][2], w.w * gh[m][3])));
+          for (int e = 0; e < MPL; ++e) gy[kb][e] = 0.f;
+        const float* w0 = sW1T + c * kQW1S;
+#pragma unroll 4
+        for (int i = 0; i < HID / 4; ++i) {
+          float4 gv[MPL];
+#pragma unroll
+          for (int e = 0; e < MPL; ++e) gv[e] = *reinterpret_cast<const float4*>(myGH + (hwi + CPL * e) * HID + 4 * i);
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            const float4 w = *reinterpret_cast<const float4*>(w0 + kb * C * kQW1S + 4 * i);
+#pragma unroll
+            for (int e = 0; e < MPL; ++e)
+              gy[kb][e] = fmaf(w.x, gv[e].x, fmaf(w.y, gv[e].y, fmaf(w.z, gv[e].z, fmaf(w.w, gv[e].w, gy[kb][e]))));
           }
         }
-#define REPB_RS_STAGE(N2, SH)                                                         \
-        {                                                                             \
-          const bool upper = (lane & SH) != 0;                                        \
-          _Pragma("unroll") for (int i = 0; i < (N2); ++i) {                          \
-            const float send = upper ? pv[i] : pv[i + (N2)];                          \
-            const float keep = upper ? pv[i + (N2)] : pv[i];                          \
-            pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, SH);                    \
-          }                                                                           \
-        }
-        REPB_RS_STAGE(32, 16) REPB_RS_STAGE(16, 8) REPB_RS_STAGE(8, 4) REPB_RS_STAGE(4, 2) REPB_RS_STAGE(2, 1)
-#undef REPB_RS_STAGE
 #pragma unroll
-        for (int e = 0; e < MPL; ++e)
-          if (valid[e]) RGs[(size_t)cellr[e] * 64 + kb * C + c] = pv[e];
+        for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+          for (int e = 0; e < MPL; ++e)
+            if (valid[e]) RGs[(size_t)cellr[e] * 64 + kb * C + c] = gy[kb][e];
       }
 #pragma unroll
       for (int r = 0; r < MPL; ++r)
         if (valid[r]) RGs[(size_t)cellr[r] * 64 + 3 * C + c] = gxs[r];
       __syncwarp();
     }
+    REPB_MARK(6);
     cl_sync_all();                                                            // ---- cluster barrier 2: RG visible
+    REPB_MARK(7);
     // ---- C: my band: g_t = gated g_{t+1} + perception^T (gy of active neighbours) + message^T (g_xs of receivers) --
     {
       const float wuni = k > 0 ? 1.0f / (float)k : 0.f;
@@ -464,6 +493,8 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       }
     }
     __syncthreads();
+    REPB_MARK(8);
+    if (R.dbg && tid == 0) s_dbg[9] += n_my;
     (void)nact;
   }
 
@@ -479,6 +510,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       if (cl < nband) R.g0[sample_off + (size_t)ch * HW + band_lo + cl] = sG[cl * C + ch];
     }
   }
+  if (R.dbg && blockIdx.x == R.dbg_cta && tid < 16) R.dbg[tid] = s_dbg[tid];
   dgam += __shfl_xor_sync(0xffffffffu, dgam, 16);
   dbet += __shfl_xor_sync(0xffffffffu, dbet, 16);
   if (lane < C) { s_chs[warp][0][lane] = dgam; s_chs[warp][1][lane] = dbet; }
@@ -735,7 +767,8 @@ __global__ void k_rep_wreduce(int nblk, int64_t total, const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 static size_t rep_bwd_smem_bytes(int C, int HW, int NC) {
   const int bandcap = ((HW + NC - 1) / NC) + 1;
-  size_t f = (size_t)3 * C * 128 + 128 + 128 * kQW2S + (size_t)bandcap * C + (size_t)kQW * 3 * C * kQG + (size_t)kQW * C * kQG;
+  size_t f = (size_t)3 * C * kQW1S + 128 + 128 * kQW2S + (size_t)bandcap * C + (size_t)kQW * 3 * C * kQG + (size_t)kQW * C * kQG +
+             (size_t)kQW * kQG * 128;
   return f * sizeof(float) + 2 * (size_t)((bandcap + 7) & ~7) * sizeof(unsigned short) + 32;
 }
 
@@ -840,11 +873,28 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = pick; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  static unsigned long long* dbg_buf = nullptr;
+  if (getenv("GNCA_PHASE_TIMING")) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), st);
+    R.dbg = dbg_buf;
+    R.dbg_cta = atoi(getenv("GNCA_PHASE_TIMING"));
+  }
   prof_begin(PROF_RESIDENT_BWD, st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, k_rep_bwd<16>, R, P, packed);
   prof_end(PROF_RESIDENT_BWD, st);
   if (e != cudaSuccess) return (int)e;
   GNCA_LAUNCH_CHECK();
+  if (R.dbg) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const char* names[10] = {"loop top", "masks+list", "A0 inactive sums", "A gz (band)", "S reduce+push", "barrier1", "B tiles",
+                             "barrier2", "C gather", "(sum n_my)"};
+    fprintf(stderr, "[gnca rep bwd phase cycles, CTA%d, T=%d]", R.dbg_cta, R.T);
+    for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
+    fprintf(stderr, "\n");
+  }
 
   // weight gradients from the records
   WgradArgs A{};
