@@ -24,6 +24,7 @@
 #include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include "gnca_common.cuh"
 #include "gnca_internal.h"
 #include "gnca_rep.h"
@@ -40,7 +41,7 @@ constexpr int kQW1S = 132;        // padded row stride of W1^T (floats): rows c,
 
 struct RepBwdArgs {
   StepArgs s;
-  int T, NC;
+  int T, NC, gmax;            // gmax: largest tile (8, or 4 when the whole sample sits in one CTA and smem is short)
   float inv_n;
   float* rec;
   const uint32_t* masks;
@@ -72,7 +73,7 @@ __device__ __forceinline__ void cl_sync_all() {
 template <int C>
 __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, const float* __restrict__ packed) {
   static_assert(C == 16, "lane mapping: 2 cells x 16 channels per warp row");
-  constexpr int C3 = 3 * C, HID = 128, G = kQG, CPL = 32 / C, MPL = G / CPL;
+  constexpr int C3 = 3 * C, HID = 128, CPL = 32 / C;
   cg::cluster_group cluster = cg::this_cluster();
   const StepArgs& a = R.s;
   const int NC = R.NC;
@@ -97,10 +98,11 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   const int band_lo = (HW * rank) >> lnc, band_hi = (HW * (rank + 1)) >> lnc, nband = band_hi - band_lo;
   const int bandcap = ((HW + NC - 1) / NC) + 1;
   float* sG = sW2P + HID * kQW2S;                             // [bandcap][C] my band of g (cell-major)
-  float* sY = sG + (size_t)bandcap * C;                       // [kQW][3C][G]
-  float* sGD = sY + kQW * C3 * G;                             // [kQW][C][G]
-  float* sGH = sGD + kQW * C * G;                             // [kQW][G][HID] gh of the tile (permuted unit order)
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(sGH + kQW * G * HID);  // [bandcap] my SHARE of the active cells
+  const int GM = R.gmax;
+  float* sY = sG + (size_t)bandcap * C;                       // [kQW][3C][GM]
+  float* sGD = sY + kQW * C3 * GM;                            // [kQW][C][GM]
+  float* sGH = sGD + kQW * C * GM;                            // [kQW][GM][HID] gh of the tile (permuted unit order)
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(sGH + kQW * GM * HID);  // [bandcap] my SHARE of the active cells
   unsigned short* s_blist = s_list + ((bandcap + 7) & ~7);                          // [bandcap] active cells of my BAND
 
   __shared__ uint32_t s_bAS[kMaskWords], s_bAct[kMaskWords], s_bPost[kMaskWords];
@@ -157,9 +159,9 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   const bool qv = q < NQ;
   const int qy = qcell / W, qx0 = qcell - qy * W;
   const int qsh = 4 * (lane & 7), qword = min(q >> 3, kMaskWords - 1);
-  float* myY = sY + warp * (C3 * G);
-  float* myGD = sGD + warp * (C * G);
-  float* myGH = sGH + warp * (G * HID);
+  float* myY = sY + warp * (C3 * GM);
+  float* myGD = sGD + warp * (C * GM);
+  float* myGH = sGH + warp * (GM * HID);
   float dgam = 0.f, dbet = 0.f;              // this lane's channel c, summed over its cells / steps
 
   for (int t = R.T - 1; t >= 0; --t) {
@@ -312,19 +314,18 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       for (int r = 0; r < NC; ++r) { s1n += s_parts[r][0]; s2n += s_parts[r][1]; }
       s1n *= R.inv_n; s2n *= R.inv_n;
     }
-    // ---- B: tiles of G cells -----------------------------------------------------------------------------------------
-    const int ntiles = (n_my + G - 1) / G;
-#pragma unroll 1
-    for (int tile = warp; tile < ntiles; tile += kQW) {
-      const int slot0 = tile * G;
+    // ---- B: my share of the active cells; every warp covers an equal contiguous range with tiles of 8 / 4 / 2 cells ---
+    auto bwd_tile = [&](auto gtag, const int slot0, const int lim) {
+      constexpr int G = decltype(gtag)::value;
+      constexpr int MPL = G / CPL;
       float gxs[MPL];
       int cellr[MPL];
       bool valid[MPL];
 #pragma unroll
       for (int r = 0; r < MPL; ++r) {
         const int m = hwi + CPL * r, sl = slot0 + m;
-        valid[r] = sl < n_my;
-        const int slc = min(sl, n_my - 1);
+        valid[r] = sl < lim;
+        const int slc = min(sl, lim - 1);
         cellr[r] = s_list[slc];
         float* rc = R.rec + (rec_base + lo_my + slc) * kRecStride;
         myY[c * G + m] = __ldcg(rc + c);
@@ -361,8 +362,17 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
 #pragma unroll 8
         for (int kk = 0; kk < C3; ++kk) {
           const float4 w = *reinterpret_cast<const float4*>(sW1T + kk * kQW1S + 4 * lane);
-          const float4 yv = *reinterpret_cast<const float4*>(myY + kk * G);
-          const float ym[4] = {yv.x, yv.y, yv.z, yv.w};
+          float ym[G];
+          if constexpr (G == 2) {
+            const float2 yv = *reinterpret_cast<const float2*>(myY + kk * G);
+            ym[0] = yv.x; ym[1] = yv.y;
+          } else {
+#pragma unroll
+            for (int m4 = 0; m4 < G / 4; ++m4) {
+              const float4 yv = *reinterpret_cast<const float4*>(myY + kk * G + 4 * m4);
+              ym[4 * m4] = yv.x; ym[4 * m4 + 1] = yv.y; ym[4 * m4 + 2] = yv.z; ym[4 * m4 + 3] = yv.w;
+            }
+          }
 #pragma unroll
           for (int m = 0; m < G; ++m) {
             acc1[m][0] = fmaf(ym[m], w.x, acc1[m][0]); acc1[m][1] = fmaf(ym[m], w.y, acc1[m][1]);
@@ -370,12 +380,12 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
           }
         }
       }
-      // gh[m][jj] = [h > 0] * sum_c W2[c][j] gd[c][m]
-      float gh[G][4];
+      // gh[m][jj] = [h > 0] * sum_c W2[c][j] gd[c][m]   (the ReLU mask as bits, the accumulators reuse acc1's registers)
+      uint32_t hmask = 0;
 #pragma unroll
       for (int m = 0; m < G; ++m)
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) gh[m][jj] = 0.f;
+        for (int jj = 0; jj < 4; ++jj) { hmask |= acc1[m][jj] > 0.f ? (1u << (4 * m + jj)) : 0u; acc1[m][jj] = 0.f; }
 #pragma unroll
       for (int c4 = 0; c4 < C / 4; ++c4) {
         float4 w2[4];
@@ -383,26 +393,35 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         for (int jj = 0; jj < 4; ++jj) w2[jj] = *reinterpret_cast<const float4*>(sW2P + (lane + 32 * jj) * kQW2S + 4 * c4);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const float4 gv = *reinterpret_cast<const float4*>(myGD + (4 * c4 + cc) * G);
-          const float gm4[4] = {gv.x, gv.y, gv.z, gv.w};
+          float gm4[G];
+          if constexpr (G == 2) {
+            const float2 gv = *reinterpret_cast<const float2*>(myGD + (4 * c4 + cc) * G);
+            gm4[0] = gv.x; gm4[1] = gv.y;
+          } else {
+#pragma unroll
+            for (int m4 = 0; m4 < G / 4; ++m4) {
+              const float4 gv = *reinterpret_cast<const float4*>(myGD + (4 * c4 + cc) * G + 4 * m4);
+              gm4[4 * m4] = gv.x; gm4[4 * m4 + 1] = gv.y; gm4[4 * m4 + 2] = gv.z; gm4[4 * m4 + 3] = gv.w;
+            }
+          }
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const float wv = cc == 0 ? w2[jj].x : cc == 1 ? w2[jj].y : cc == 2 ? w2[jj].z : w2[jj].w;
 #pragma unroll
-            for (int m = 0; m < G; ++m) gh[m][jj] = fmaf(wv, gm4[m], gh[m][jj]);
+            for (int m = 0; m < G; ++m) acc1[m][jj] = fmaf(wv, gm4[m], acc1[m][jj]);
           }
         }
       }
-#pragma unroll
-      for (int m = 0; m < G; ++m)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) gh[m][jj] = acc1[m][jj] > 0.f ? gh[m][jj] : 0.f;
       // gy[kk][m] = sum_j W1[j][kk] gh[j][m].  gh goes through the warp's shared-memory tile so that the lane that owns
       // (cell hwi+2e, channel c) can run the three 128-long dot products itself (rows c, 16+c, 32+c of W1^T = identity /
       // sobel_x / sobel_y parts): no cross-lane reduction.
 #pragma unroll
-      for (int m = 0; m < G; ++m)
-        *reinterpret_cast<float4*>(myGH + m * HID + 4 * lane) = make_float4(gh[m][0], gh[m][1], gh[m][2], gh[m][3]);
+      for (int m = 0; m < G; ++m) {
+        float4 v;
+        v.x = (hmask >> (4 * m)) & 1u ? acc1[m][0] : 0.f; v.y = (hmask >> (4 * m + 1)) & 1u ? acc1[m][1] : 0.f;
+        v.z = (hmask >> (4 * m + 2)) & 1u ? acc1[m][2] : 0.f; v.w = (hmask >> (4 * m + 3)) & 1u ? acc1[m][3] : 0.f;
+        *reinterpret_cast<float4*>(myGH + m * HID + 4 * lane) = v;
+      }
       __syncwarp();
       {
         float gy[3][MPL];
@@ -411,7 +430,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
 #pragma unroll
           for (int e = 0; e < MPL; ++e) gy[kb][e] = 0.f;
         const float* w0 = sW1T + c * kQW1S;
-#pragma unroll 4
+#pragma unroll 2
         for (int i = 0; i < HID / 4; ++i) {
           float4 gv[MPL];
 #pragma unroll
@@ -434,6 +453,16 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       for (int r = 0; r < MPL; ++r)
         if (valid[r]) RGs[(size_t)cellr[r] * 64 + 3 * C + c] = gxs[r];
       __syncwarp();
+    };
+    {
+      const int w_lo = (n_my * warp) >> 4, w_hi = (n_my * (warp + 1)) >> 4;
+#pragma unroll 1
+      for (int s0 = w_lo; s0 < w_hi;) {
+        const int rem = w_hi - s0;
+        if (rem > 4 && R.gmax >= 8) { bwd_tile(std::integral_constant<int, 8>{}, s0, w_hi); s0 += 8; }
+        else if (rem > 2) { bwd_tile(std::integral_constant<int, 4>{}, s0, w_hi); s0 += 4; }
+        else { bwd_tile(std::integral_constant<int, 2>{}, s0, w_hi); s0 += 2; }
+      }
     }
     REPB_MARK(6);
     cl_sync_all();                                                            // ---- cluster barrier 2: RG visible
@@ -448,40 +477,79 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         const int cell = band_lo + cl, py = cell / W, px = cell - py * W;
         float4 g = *reinterpret_cast<const float4*>(sG + cl * C + 4 * cq);
         if (cq == 0 && !((s_bPost[cell >> 5] >> (cell & 31)) & 1u)) g.w = 0.f;
+        // active neighbours as a 9-bit mask, then ALL loads of the item are issued before the first use (predicated, no
+        // branches between them): one L2 round trip per item instead of one per neighbour
+        uint32_t nbm = 0;
 #pragma unroll
-        for (int ay = -1; ay <= 1; ++ay) {
+        for (int ay = -1; ay <= 1; ++ay)
 #pragma unroll
           for (int ax = -1; ax <= 1; ++ax) {
             const int yy = py + ay, xx = px + ax;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const int ac = yy * W + xx;
-            if (!actbit(ac)) continue;
-            const float* rg = RGs + (size_t)ac * 64 + 4 * cq;
-            const float kx = (ax == 0 ? 0.f : (ax > 0 ? 1.f : -1.f)) * (ay == 0 ? 2.f : 1.f);
-            const float ky = (ay == 0 ? 0.f : (ay > 0 ? 1.f : -1.f)) * (ax == 0 ? 2.f : 1.f);
-            if (ay == 0 && ax == 0) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(rg));
-              g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+            const bool inb = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const int ac = inb ? yy * W + xx : cell;
+            nbm |= (inb && actbit(ac)) ? (1u << ((ay + 1) * 3 + (ax + 1))) : 0u;
+          }
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 vid = z4, vsx[6], vsy[6];
+        if (nbm & (1u << 4)) vid = __ldcg(reinterpret_cast<const float4*>(RGs + (size_t)cell * 64 + 4 * cq));
+        {
+          int ix = 0, iy = 0;
+#pragma unroll
+          for (int ay = -1; ay <= 1; ++ay)
+#pragma unroll
+            for (int ax = -1; ax <= 1; ++ax) {
+              const bool on = (nbm >> ((ay + 1) * 3 + (ax + 1))) & 1u;
+              const float* rg = RGs + (size_t)(cell + ay * W + ax) * 64 + 4 * cq;
+              if (ax != 0) { vsx[ix] = on ? __ldcg(reinterpret_cast<const float4*>(rg + C)) : z4; ++ix; }
+              if (ay != 0) { vsy[iy] = on ? __ldcg(reinterpret_cast<const float4*>(rg + 2 * C)) : z4; ++iy; }
             }
-            if (kx != 0.f) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(rg + C));
-              g.x = fmaf(kx, v.x, g.x); g.y = fmaf(kx, v.y, g.y); g.z = fmaf(kx, v.z, g.z); g.w = fmaf(kx, v.w, g.w);
-            }
-            if (ky != 0.f) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(rg + 2 * C));
-              g.x = fmaf(ky, v.x, g.x); g.y = fmaf(ky, v.y, g.y); g.z = fmaf(ky, v.z, g.z); g.w = fmaf(ky, v.w, g.w);
+        }
+        uint32_t rm = 0;
+        int rcell[16];
+        const bool sender = msg_on && (!a2a || ((s_bAS[cell >> 5] >> (cell & 31)) & 1u));
+        if (sender) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            rcell[i] = cell;
+            if (i < k) {
+              int ry = py + (int)s_off[2 * i], rx = px + (int)s_off[2 * i + 1];
+              ry += ry < 0 ? H : 0; ry -= ry >= H ? H : 0;
+              rx += rx < 0 ? W : 0; rx -= rx >= W ? W : 0;
+              rcell[i] = ry * W + rx;
+              rm |= actbit(rcell[i]) ? (1u << i) : 0u;
             }
           }
         }
-        if (msg_on && (!a2a || ((s_bAS[cell >> 5] >> (cell & 31)) & 1u))) {
-          for (int i = 0; i < k; ++i) {
-            int ry = py + (int)s_off[2 * i], rx = px + (int)s_off[2 * i + 1];
-            ry += ry < 0 ? H : 0; ry -= ry >= H ? H : 0;
-            rx += rx < 0 ? W : 0; rx -= rx >= W ? W : 0;
-            const int rc = ry * W + rx;
-            if (!actbit(rc)) continue;
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(RGs + (size_t)rc * 64 + 3 * C + 4 * cq));
-            g.x = fmaf(wuni, v.x, g.x); g.y = fmaf(wuni, v.y, g.y); g.z = fmaf(wuni, v.z, g.z); g.w = fmaf(wuni, v.w, g.w);
+        g.x += vid.x; g.y += vid.y; g.z += vid.z; g.w += vid.w;
+        {
+          int ix = 0, iy = 0;
+#pragma unroll
+          for (int ay = -1; ay <= 1; ++ay)
+#pragma unroll
+            for (int ax = -1; ax <= 1; ++ax) {
+              if (ax != 0) {
+                const float kx = (ax > 0 ? 1.f : -1.f) * (ay == 0 ? 2.f : 1.f);
+                g.x = fmaf(kx, vsx[ix].x, g.x); g.y = fmaf(kx, vsx[ix].y, g.y);
+                g.z = fmaf(kx, vsx[ix].z, g.z); g.w = fmaf(kx, vsx[ix].w, g.w);
+                ++ix;
+              }
+              if (ay != 0) {
+                const float ky = (ay > 0 ? 1.f : -1.f) * (ax == 0 ? 2.f : 1.f);
+                g.x = fmaf(ky, vsy[iy].x, g.x); g.y = fmaf(ky, vsy[iy].y, g.y);
+                g.z = fmaf(ky, vsy[iy].z, g.z); g.w = fmaf(ky, vsy[iy].w, g.w);
+                ++iy;
+              }
+            }
+        }
+        if (rm) {
+          float4 vr[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            vr[i] = (rm >> i) & 1u ? __ldcg(reinterpret_cast<const float4*>(RGs + (size_t)rcell[i] * 64 + 3 * C + 4 * cq)) : z4;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            g.x = fmaf(wuni, vr[i].x, g.x); g.y = fmaf(wuni, vr[i].y, g.y);
+            g.z = fmaf(wuni, vr[i].z, g.z); g.w = fmaf(wuni, vr[i].w, g.w);
           }
         }
         if (dmg) {
@@ -765,10 +833,10 @@ __global__ void k_rep_wreduce(int nblk, int64_t total, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-static size_t rep_bwd_smem_bytes(int C, int HW, int NC) {
+static size_t rep_bwd_smem_bytes(int C, int HW, int NC, int gmax) {
   const int bandcap = ((HW + NC - 1) / NC) + 1;
-  size_t f = (size_t)3 * C * kQW1S + 128 + 128 * kQW2S + (size_t)bandcap * C + (size_t)kQW * 3 * C * kQG + (size_t)kQW * C * kQG +
-             (size_t)kQW * kQG * 128;
+  size_t f = (size_t)3 * C * kQW1S + 128 + 128 * kQW2S + (size_t)bandcap * C + (size_t)kQW * 3 * C * gmax + (size_t)kQW * C * gmax +
+             (size_t)kQW * gmax * 128;
   return f * sizeof(float) + 2 * (size_t)((bandcap + 7) & ~7) * sizeof(unsigned short) + 32;
 }
 
@@ -834,14 +902,16 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
 
   const char* env_nc = getenv("GNCA_RESIDENT_NC");
   const int cands[4] = {8, 4, 2, 1};
-  int pick = -1;
+  int pick = -1, pick_gmax = 8;
   size_t pick_smem = 0;
   for (int pass = 0; pass < 2 && pick < 0; ++pass) {
     for (int ci = (pass == 0 ? 0 : 3); ci >= 0 && ci < 4; ci += (pass == 0 ? 1 : -1)) {
       const int NC = cands[ci];
       if (env_nc && atoi(env_nc) != NC) continue;
       if ((HW % (4 * NC)) != 0) continue;                 // bands start at a quad boundary
-      const size_t smem = rep_bwd_smem_bytes(C, HW, NC);
+      int gmax = 8;
+      size_t smem = rep_bwd_smem_bytes(C, HW, NC, gmax);
+      if (smem > 226 * 1024) { gmax = 4; smem = rep_bwd_smem_bytes(C, HW, NC, gmax); }
       if (smem > 226 * 1024) continue;
       GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cudaLaunchConfig_t q{};
@@ -856,12 +926,12 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
         continue;
       }
       if (pass == 0 && B > ncl && !env_nc) continue;
-      pick = NC; pick_smem = smem;
+      pick = NC; pick_smem = smem; pick_gmax = gmax;
       break;
     }
   }
   if (pick < 0) return GNCA_ERR_UNSUPPORTED;
-  R.NC = pick;
+  R.NC = pick; R.gmax = pick_gmax;
   if (getenv("GNCA_DEBUG")) fprintf(stderr, "[gnca] resident bwd: B=%d NC=%d smem=%zu\n", B, pick, pick_smem);
   GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pick_smem));
   cudaLaunchConfig_t cfg{};
