@@ -61,7 +61,8 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
                 float* u_hist, float* rec, uint32_t* masks, float* scratch, cudaStream_t st);
 // resident BPTT on the records of run_rep_fwd (gnca_rep_bwd.cu)
 size_t rep_bptt_bytes(const gnca_model& m, int B, int H, int W, int T);     // 0: configuration not supported
-void rep_bptt_carve(void* base, int B, int H, int W, int T, float** rec, uint32_t** masks, float** stats);
+void rep_bptt_carve(void* base, int B, int H, int W, int T, float** rec, uint32_t** masks, float** stats,
+                    float** hgh = nullptr);
 size_t rep_bwd_workspace_bytes(const gnca_model& m, int B, int H, int W);
 int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,
                 const gnca_schedule& sched, void* bptt, const float* gT, float* g0, float* gparams, void* workspace,

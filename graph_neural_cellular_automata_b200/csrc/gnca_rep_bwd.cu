@@ -44,6 +44,7 @@ struct RepBwdArgs {
   int T, NC, gmax;            // gmax: largest tile (8, or 4 when the whole sample sits in one CTA and smem is short)
   float inv_n;
   float* rec;
+  float* hgh;                 // [T][B][HW][kHghStride] h | gh of every record (written here, read by k_rep_wgrad)
   const uint32_t* masks;
   const float* stats;         // [T][B][2]
   const float* gT;            // [B][C][HW]
@@ -383,9 +384,13 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       // gh[m][jj] = [h > 0] * sum_c W2[c][j] gd[c][m]   (the ReLU mask as bits, the accumulators reuse acc1's registers)
       uint32_t hmask = 0;
 #pragma unroll
-      for (int m = 0; m < G; ++m)
+      for (int m = 0; m < G; ++m) {
+        if (slot0 + m < lim)
+          *reinterpret_cast<float4*>(R.hgh + (rec_base + lo_my + slot0 + m) * kHghStride + 4 * lane) =
+              make_float4(fmaxf(acc1[m][0], 0.f), fmaxf(acc1[m][1], 0.f), fmaxf(acc1[m][2], 0.f), fmaxf(acc1[m][3], 0.f));
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) { hmask |= acc1[m][jj] > 0.f ? (1u << (4 * m + jj)) : 0u; acc1[m][jj] = 0.f; }
+      }
 #pragma unroll
       for (int c4 = 0; c4 < C / 4; ++c4) {
         float4 w2[4];
@@ -421,6 +426,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         v.x = (hmask >> (4 * m)) & 1u ? acc1[m][0] : 0.f; v.y = (hmask >> (4 * m + 1)) & 1u ? acc1[m][1] : 0.f;
         v.z = (hmask >> (4 * m + 2)) & 1u ? acc1[m][2] : 0.f; v.w = (hmask >> (4 * m + 3)) & 1u ? acc1[m][3] : 0.f;
         *reinterpret_cast<float4*>(myGH + m * HID + 4 * lane) = v;
+        if (slot0 + m < lim) *reinterpret_cast<float4*>(R.hgh + (rec_base + lo_my + slot0 + m) * kHghStride + HID + 4 * lane) = v;
       }
       __syncwarp();
       {
@@ -597,11 +603,11 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
 // ------------------------------------------------------------------------------------------------
 constexpr int kWT = 256;          // threads
 constexpr int kWNB = 32;          // records per batch
-constexpr int kWNBP = kWNB + 4;
 constexpr int kWMaxSeg = 256;     // (t, b) segments per block and round
 
 struct WgradArgs {
   const float* rec;
+  const float* hgh;
   const uint32_t* masks;
   const int32_t* steps;       // [B] or null
   int T, B, HW, NW;
@@ -611,9 +617,6 @@ struct WgradArgs {
   gnca_layout L;
 };
 
-__device__ __forceinline__ float dot4f(const float4& a, const float4& b) {
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
-}
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -621,49 +624,33 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// dW1 += gh (x) y, db1 += gh, dW2 += gd (x) h, dWm += gm (x) xs, dbm += gm * as over all records: operands are read
+// record-major straight from the cp.async buffers (a thread's 4 hidden units are one float4 of the permuted h / gh rows).
 template <int C>
-__global__ void __launch_bounds__(kWT, 2) k_rep_wgrad(WgradArgs A, Packed P, const float* __restrict__ packed) {
-  constexpr int C3 = 3 * C, HID = 128, NB = kWNB, NBP = kWNBP;
-  constexpr int TK = 6, KG = C3 / TK;          // dW1 tile: 4 hidden units x 6 inputs per thread (JQ*KG = 32*8 = 256 threads)
+__global__ void __launch_bounds__(kWT, 2) k_rep_wgrad(WgradArgs A) {
+  constexpr int C3 = 3 * C, HID = 128, NB = kWNB;
+  constexpr int TK = 6, KG = C3 / TK;          // dW1 tile: 4 hidden units (one permuted float4) x 6 consecutive inputs
   constexpr int JQ = HID / 4;
-  constexpr int RAWF = NB * kRecStride;        // floats of one raw batch
+  constexpr int RAWR = NB * kRecStride, RAWH = NB * kHghStride;
   static_assert(JQ * KG == kWT, "dW1 tiling");
-  static_assert((NB / 4) * (HID / 4) == kWT, "G1 tiling: one 4x4 tile per thread");
   const bool graph = (A.flags & GNCA_F_GRAPH) != 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sW1T = reinterpret_cast<float*>(smem_raw);     // [3C][HID]
-  float* sb1 = sW1T + C3 * HID;
-  float* sW2 = sb1 + HID;                               // [C][HID]
-  float* RAW = sW2 + C * HID;                           // [2][NB][kRecStride] record-major double buffer (cp.async)
-  float* Yt = RAW + 2 * RAWF;                           // [3C][NBP] feature-major
-  float* GDt = Yt + C3 * NBP;                           // [C][NBP]
-  float* XSt = GDt + C * NBP;                           // [C][NBP]
-  float* GMt = XSt + C * NBP;                           // [C][NBP]
-  float* ASv = GMt + C * NBP;                           // [NBP]
-  float* Ht = ASv + NBP;                                // [HID][NBP]
-  float* GHt = Ht + HID * NBP;                          // [HID][NBP]
+  float* RAW = reinterpret_cast<float*>(smem_raw);      // [2][NB][kRecStride]
+  float* RH = RAW + 2 * RAWR;                           // [2][NB][kHghStride]
   __shared__ int s_cnt[kWMaxSeg];
   const int tid = threadIdx.x;
-  block_copy(sW1T, packed + P.w1t, C3 * HID);
-  block_copy(sb1, packed + P.b1, HID);
-  block_copy(sW2, packed + P.w2, C * HID);
 
-  // persistent accumulators
-  float aW1[4][TK], ab1[4], aW2[2][4], aWm = 0.f, abm = 0.f;
+  float aW1[4][TK], ab1[4], aW2[4][2], aWm = 0.f, abm = 0.f;
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj) { ab1[jj] = 0.f; for (int kk = 0; kk < TK; ++kk) aW1[jj][kk] = 0.f; }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) for (int jj = 0; jj < 4; ++jj) aW2[i][jj] = 0.f;
-  const int kg = tid % KG, jg = tid / KG;               // dW1: j = jg + JQ*jj, k = kg + KG*kk
-  const int cq2 = tid % (C / 2), jg2 = tid / (C / 2);   // dW2: c = cq2 + 8*i, j = jg2 + JQ*jj   (8 * 32 = 256 threads)
+  for (int jj = 0; jj < 4; ++jj) { ab1[jj] = 0.f; aW2[jj][0] = aW2[jj][1] = 0.f; for (int kk = 0; kk < TK; ++kk) aW1[jj][kk] = 0.f; }
+  const int kg = tid % KG, jg = tid / KG;               // dW1: units jg + 32 jj (float4 at 4 jg), inputs 6 kg .. 6 kg + 5
+  const int cp2 = tid % (C / 2), jg2 = tid / (C / 2);   // dW2: channels 2 cp2, 2 cp2 + 1, units jg2 + 32 jj
   const int mc = tid / C, mci = tid % C;                // dWm[mc][mci]
-  const int cgp = tid % (NB / 4), jt = tid / (NB / 4);  // G1/G2: cells 4cgp.., hidden units 4jt..
 
   const int nseg = A.T * A.B;
   for (int seg0 = blockIdx.x; seg0 < nseg; seg0 += gridDim.x * kWMaxSeg) {
-    // record counts of my segments of this round (popcount of the active bitmap)
     __syncthreads();
-    for (int si = tid; si < kWMaxSeg; si += kWT) {
+    for (int si = tid; si < kWMaxSeg; si += kWT) {        // record counts of my segments (popcount of the active bitmap)
       const int seg = seg0 + si * gridDim.x;
       int cnt = 0;
       if (seg < nseg) {
@@ -676,7 +663,6 @@ __global__ void __launch_bounds__(kWT, 2) k_rep_wgrad(WgradArgs A, Packed P, con
       s_cnt[si] = cnt;
     }
     __syncthreads();
-    // flat walk over (segment, batch) with one batch of look-ahead
     int si = 0, base = 0;
     auto skip_empty = [&](int& s_, int& b_) { while (s_ < kWMaxSeg && b_ >= s_cnt[s_]) { ++s_; b_ = 0; } };
     auto issue = [&](int s_, int b_, int buf) {
@@ -684,8 +670,11 @@ __global__ void __launch_bounds__(kWT, 2) k_rep_wgrad(WgradArgs A, Packed P, con
         const int seg = seg0 + s_ * gridDim.x;
         const int nb = min(NB, s_cnt[s_] - b_);
         const float* src = A.rec + ((size_t)seg * A.HW + b_) * kRecStride;
-        float* dst = RAW + buf * RAWF;
+        const float* srch = A.hgh + ((size_t)seg * A.HW + b_) * kHghStride;
+        float* dst = RAW + buf * RAWR;
+        float* dsth = RH + buf * RAWH;
         for (int i = tid; i < nb * (kRecStride / 4); i += kWT) cp_async16(dst + 4 * i, src + 4 * i);
+        for (int i = tid; i < nb * (kHghStride / 4); i += kWT) cp_async16(dsth + 4 * i, srch + 4 * i);
       }
       cp_async_commit();
     };
@@ -698,122 +687,54 @@ __global__ void __launch_bounds__(kWT, 2) k_rep_wgrad(WgradArgs A, Packed P, con
       skip_empty(nsi, nbase);
       issue(nsi, nbase, buf ^ 1);
       cp_async_wait<1>();
-      __syncthreads();                                   // raw batch landed; previous batch's tiles fully consumed
-      // record-major raw -> feature-major tiles (zero padded to NB cells)
-      {
-        const float* raw = RAW + buf * RAWF;
-        for (int i = tid; i < NB * kRecStride; i += kWT) {
-          const int cl = i % NB, f = i / NB;
-          const float v = cl < nb ? raw[cl * kRecStride + f] : 0.f;
-          if (f < C3) Yt[f * NBP + cl] = v;
-          else if (f < kRecXs) GDt[(f - kRecU) * NBP + cl] = v;
-          else if (f < kRecTh) XSt[(f - kRecXs) * NBP + cl] = v;
-          else if (f < kRecAs) GMt[(f - kRecTh) * NBP + cl] = v;
-          else if (f == kRecAs) ASv[cl] = v;
-        }
-      }
-      __syncthreads();
-      // G1/G2: h = relu(W1 y + b1), gh = (W2^T gd) * [h > 0]: one 4 cells x 4 units tile per thread
-      {
-        const int j = jt * 4;
-        float acc[4][4], g2[4][4];
-        const float4 bb = *reinterpret_cast<const float4*>(sb1 + j);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          acc[m][0] = bb.x; acc[m][1] = bb.y; acc[m][2] = bb.z; acc[m][3] = bb.w;
-          g2[m][0] = g2[m][1] = g2[m][2] = g2[m][3] = 0.f;
-        }
-#pragma unroll 8
-        for (int kk = 0; kk < C3; ++kk) {
-          const float4 yv = *reinterpret_cast<const float4*>(Yt + kk * NBP + 4 * cgp);
-          const float4 w = *reinterpret_cast<const float4*>(sW1T + kk * HID + j);
-          const float ym[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            acc[m][0] = fmaf(ym[m], w.x, acc[m][0]); acc[m][1] = fmaf(ym[m], w.y, acc[m][1]);
-            acc[m][2] = fmaf(ym[m], w.z, acc[m][2]); acc[m][3] = fmaf(ym[m], w.w, acc[m][3]);
-          }
-        }
-#pragma unroll 8
-        for (int cc = 0; cc < C; ++cc) {
-          const float4 gv = *reinterpret_cast<const float4*>(GDt + cc * NBP + 4 * cgp);
-          const float4 w = *reinterpret_cast<const float4*>(sW2 + cc * HID + j);
-          const float gm[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            g2[m][0] = fmaf(gm[m], w.x, g2[m][0]); g2[m][1] = fmaf(gm[m], w.y, g2[m][1]);
-            g2[m][2] = fmaf(gm[m], w.z, g2[m][2]); g2[m][3] = fmaf(gm[m], w.w, g2[m][3]);
-          }
-        }
+      __syncthreads();                                   // this batch has landed
+      const float* raw = RAW + buf * RAWR;
+      const float* rh = RH + buf * RAWH;
+#pragma unroll 2
+      for (int cl = 0; cl < nb; ++cl) {
+        const float* rc = raw + cl * kRecStride;
+        const float4 g = *reinterpret_cast<const float4*>(rh + cl * kHghStride + HID + 4 * jg);
+        const float2 y01 = *reinterpret_cast<const float2*>(rc + TK * kg);
+        const float2 y23 = *reinterpret_cast<const float2*>(rc + TK * kg + 2);
+        const float2 y45 = *reinterpret_cast<const float2*>(rc + TK * kg + 4);
+        const float gj[4] = {g.x, g.y, g.z, g.w};
+        const float yk[TK] = {y01.x, y01.y, y23.x, y23.y, y45.x, y45.y};
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          float4 hv, gv;
-          hv.x = fmaxf(acc[0][jj], 0.f); hv.y = fmaxf(acc[1][jj], 0.f);
-          hv.z = fmaxf(acc[2][jj], 0.f); hv.w = fmaxf(acc[3][jj], 0.f);
-          gv.x = acc[0][jj] > 0.f ? g2[0][jj] : 0.f; gv.y = acc[1][jj] > 0.f ? g2[1][jj] : 0.f;
-          gv.z = acc[2][jj] > 0.f ? g2[2][jj] : 0.f; gv.w = acc[3][jj] > 0.f ? g2[3][jj] : 0.f;
-          *reinterpret_cast<float4*>(Ht + (j + jj) * NBP + 4 * cgp) = hv;
-          *reinterpret_cast<float4*>(GHt + (j + jj) * NBP + 4 * cgp) = gv;
+#pragma unroll
+          for (int kk = 0; kk < TK; ++kk) aW1[jj][kk] = fmaf(gj[jj], yk[kk], aW1[jj][kk]);
+          if (kg == 0) ab1[jj] += gj[jj];
+        }
+        const float4 hv = *reinterpret_cast<const float4*>(rh + cl * kHghStride + 4 * jg2);
+        const float2 gd2 = *reinterpret_cast<const float2*>(rc + kRecU + 2 * cp2);
+        const float hj[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          aW2[jj][0] = fmaf(gd2.x, hj[jj], aW2[jj][0]);
+          aW2[jj][1] = fmaf(gd2.y, hj[jj], aW2[jj][1]);
+        }
+        if (graph) {
+          const float gmv = rc[kRecTh + mc];
+          aWm = fmaf(gmv, rc[kRecXs + mci], aWm);
+          if (mci == 0) abm = fmaf(gmv, rc[kRecAs], abm);
         }
       }
-      __syncthreads();
-      // dW1 += GH^T Y, db1 += colsum(GH)   (padding cells have gd = 0 -> gh = 0)
-#pragma unroll 2
-      for (int c4 = 0; c4 < NB / 4; ++c4) {
-        float4 g[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) g[jj] = *reinterpret_cast<const float4*>(GHt + (jg + JQ * jj) * NBP + 4 * c4);
-#pragma unroll
-        for (int kk = 0; kk < TK; ++kk) {
-          const float4 yv = *reinterpret_cast<const float4*>(Yt + (kg + KG * kk) * NBP + 4 * c4);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) aW1[jj][kk] += dot4f(g[jj], yv);
-        }
-        if (kg == 0) {
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) ab1[jj] += (g[jj].x + g[jj].y) + (g[jj].z + g[jj].w);
-        }
-      }
-      // dW2 += GD^T H
-#pragma unroll 2
-      for (int c4 = 0; c4 < NB / 4; ++c4) {
-        float4 hh[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) hh[jj] = *reinterpret_cast<const float4*>(Ht + (jg2 + JQ * jj) * NBP + 4 * c4);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float4 gv = *reinterpret_cast<const float4*>(GDt + (cq2 + (C / 2) * i) * NBP + 4 * c4);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) aW2[i][jj] += dot4f(gv, hh[jj]);
-        }
-      }
-      // dWm += GM^T XS, dbm += GM . AS   (graph_augmentation.py:57 msg_proj)
-      if (graph) {
-#pragma unroll
-        for (int c4 = 0; c4 < NB / 4; ++c4) {
-          const float4 gmv = *reinterpret_cast<const float4*>(GMt + mc * NBP + 4 * c4);
-          const float4 xv = *reinterpret_cast<const float4*>(XSt + mci * NBP + 4 * c4);
-          aWm += dot4f(gmv, xv);
-          if (mci == 0) abm += dot4f(gmv, *reinterpret_cast<const float4*>(ASv + 4 * c4));
-        }
-      }
+      __syncthreads();                                   // everybody is done with this buffer before it is refilled
       si = nsi; base = nbase; buf ^= 1;
     }
     cp_async_wait<0>();
   }
-  // one partial per block (canonical layout); the block's row was zeroed by the launcher
+  // one partial per block (canonical layout)
   float* wp = A.wpart + (size_t)blockIdx.x * A.wtotal;
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
     const int j = jg + JQ * jj;
 #pragma unroll
-    for (int kk = 0; kk < TK; ++kk) wp[A.L.w1 + (int64_t)j * C3 + (kg + KG * kk)] = aW1[jj][kk];
+    for (int kk = 0; kk < TK; ++kk) wp[A.L.w1 + (int64_t)j * C3 + (TK * kg + kk)] = aW1[jj][kk];
     if (kg == 0) wp[A.L.b1 + j] = ab1[jj];
+    wp[A.L.w2 + (int64_t)(2 * cp2) * HID + (jg2 + JQ * jj)] = aW2[jj][0];
+    wp[A.L.w2 + (int64_t)(2 * cp2 + 1) * HID + (jg2 + JQ * jj)] = aW2[jj][1];
   }
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) wp[A.L.w2 + (int64_t)(cq2 + (C / 2) * i) * HID + (jg2 + JQ * jj)] = aW2[i][jj];
   if (graph) {
     wp[A.L.wm + mc * C + mci] = aWm;
     if (mci == 0) wp[A.L.bm + mc] = abm;
@@ -845,17 +766,20 @@ size_t rep_bptt_bytes(const gnca_model& m, int B, int H, int W, int T) {
   const size_t HW = (size_t)H * W;
   size_t bytes = (size_t)T * B * HW * kRecStride * sizeof(float);
   bytes = (bytes + 255) & ~(size_t)255;
+  bytes += (size_t)T * B * HW * kHghStride * sizeof(float);
   bytes += (size_t)T * B * 3 * kMaskWords * sizeof(uint32_t);
   bytes += (size_t)T * B * 2 * sizeof(float) + 256;
   return bytes;
 }
 
-void rep_bptt_carve(void* base, int B, int H, int W, int T, float** rec, uint32_t** masks, float** stats) {
+void rep_bptt_carve(void* base, int B, int H, int W, int T, float** rec, uint32_t** masks, float** stats, float** hgh) {
   const size_t HW = (size_t)H * W;
   char* p = reinterpret_cast<char*>(base);
   size_t o = (size_t)T * B * HW * kRecStride * sizeof(float);
   o = (o + 255) & ~(size_t)255;
   *rec = reinterpret_cast<float*>(p);
+  if (hgh) *hgh = reinterpret_cast<float*>(p + o);
+  o += (size_t)T * B * HW * kHghStride * sizeof(float);
   *masks = reinterpret_cast<uint32_t*>(p + o);
   o += (size_t)T * B * 3 * kMaskWords * sizeof(uint32_t);
   *stats = reinterpret_cast<float*>(p + o);
@@ -878,9 +802,9 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
   if (graph && k > 0 && !(m.flags & GNCA_F_TORUS)) return GNCA_ERR_UNSUPPORTED;
   if (k > 16) return GNCA_ERR_UNSUPPORTED;
   const int C = 16, HW = H * W;
-  float *rec, *stats;
+  float *rec, *stats, *hgh;
   uint32_t* masks;
-  rep_bptt_carve(bptt, B, H, W, sched.T, &rec, &masks, &stats);
+  rep_bptt_carve(bptt, B, H, W, sched.T, &rec, &masks, &stats, &hgh);
   const gnca_layout L = make_layout(m);
   float* ws = reinterpret_cast<float*>(workspace);
   float* GZ = ws; ws += (size_t)B * HW * C;
@@ -896,7 +820,7 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
   R.s.steps = sched.steps;
   R.T = sched.T;
   R.inv_n = (float)(1.0 / ((double)C * (double)H * (double)W));
-  R.rec = rec; R.masks = masks; R.stats = stats; R.gT = gT; R.g0 = g0; R.GZ = GZ; R.RG = RG;
+  R.rec = rec; R.hgh = hgh; R.masks = masks; R.stats = stats; R.gT = gT; R.g0 = g0; R.GZ = GZ; R.RG = RG;
   R.affpart = affpart;
   R.damage = sched.damage; R.damage_step = sched.damage_step;
 
@@ -968,17 +892,16 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
 
   // weight gradients from the records
   WgradArgs A{};
-  A.rec = rec; A.masks = masks; A.steps = sched.steps; A.T = sched.T; A.B = B; A.HW = HW; A.NW = (HW + 31) >> 5;
+  A.rec = rec; A.hgh = hgh; A.masks = masks; A.steps = sched.steps; A.T = sched.T; A.B = B; A.HW = HW; A.NW = (HW + 31) >> 5;
   A.flags = m.flags; A.wpart = wpart; A.wtotal = L.total; A.L = L;
   int nseg = sched.T * B;
   int nblk = nseg < kMaxWgradBlocks ? nseg : kMaxWgradBlocks;
   if (nblk < 1) nblk = 1;
   GNCA_CHECK_CUDA(cudaMemsetAsync(wpart, 0, (size_t)nblk * L.total * sizeof(float), st));
-  const size_t wsmem = ((size_t)3 * C * 128 + 128 + (size_t)C * 128 + 2 * (size_t)kWNB * kRecStride +
-                        (size_t)(3 * C + 3 * C) * kWNBP + kWNBP + 2 * (size_t)128 * kWNBP) * sizeof(float);
+  const size_t wsmem = 2 * (size_t)kWNB * (kRecStride + kHghStride) * sizeof(float);
   GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_wgrad<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
   prof_begin(PROF_BWD_MLP, st);
-  k_rep_wgrad<16><<<nblk, kWT, wsmem, st>>>(A, P, packed);
+  k_rep_wgrad<16><<<nblk, kWT, wsmem, st>>>(A);
   prof_end(PROF_BWD_MLP, st);
   GNCA_LAUNCH_CHECK();
   k_rep_wreduce<<<(int)((L.total + 255) / 256), 256, 0, st>>>(nblk, L.total, wpart, B * pick, C, affpart, L, gparams);
