@@ -304,7 +304,7 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
 
     # ---------------- roofline of the dominant kernel (library event hook), rank 0 ----------------
     roof = None
-    if rank == 0 and with_roofline:
+    if with_roofline:            # every rank runs these iterations (the training step holds a collective); rank 0 reports
         lib.gnca_profile_enable(1)
         nprof = min(steps, 5)
         for i in range(nprof):
