@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libgnca.so")
 GNCA_F_GRAPH, GNCA_F_TORUS, GNCA_F_HIDDEN_ONLY, GNCA_F_ALIVE_TO_ALIVE, GNCA_F_GROUPNORM = 1, 2, 4, 8, 16
 GNCA_MAX_K = 64
 GNCA_ERR_ARG, GNCA_ERR_UNSUPPORTED = -1, -2
-GNCA_VERSION = 103
+GNCA_VERSION = 104
 
 
 class GncaModel(C.Structure):
@@ -74,6 +74,7 @@ EXPORTS = {
     "gnca_rollout_bwd_bptt": (C.c_int, [C.POINTER(GncaModel), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.POINTER(GncaSchedule), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnca_host_sample_indices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gnca_loss_premult_rgba": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 4 + [C.c_float, C.c_void_p]),
     "gnca_normalize_adam": (C.c_int, [C.c_void_p] * 4 + [C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),

@@ -242,4 +242,52 @@ int gnca_rollout_bwd_bptt(const gnca_model* m, const float* packed_dev, int B, i
   return run_rep_bwd(*m, P, packed_dev, B, H, W, *sched, bptt_dev, gT_dev, g0_dev, gparams_dev, workspace_dev,
                      (cudaStream_t)stream);
 }
+
+/* ---- host-side schedule construction: T x random.sample(range(n), k) on CPython's MT19937 state ----
+ * CPython: random.sample on a short population is a partial Fisher-Yates over a copy of the population driven by
+ * _randbelow(m) = { k = m.bit_length(); do r = getrandbits(k) while (r >= m); }, getrandbits(k <= 32) =
+ * genrand_uint32() >> (32 - k)   (Lib/random.py, Modules/_randommodule.c).  `mt` is the 624-word state, *mti the
+ * position (the 625th element of random.getstate()[1]); both are advanced in place. */
+int gnca_host_sample_indices(uint32_t* mt, int32_t* mti, int n, int k, int T, int32_t* out_idx) {
+  if (!mt || !mti || !out_idx || n <= 0 || k < 0 || k > n || n > 4096 || T < 0) return GNCA_ERR_ARG;
+  int pos = *mti;
+  auto next_u32 = [&]() -> uint32_t {
+    if (pos >= 624) {
+      const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX = 0x9908b0dfu;
+      int kk;
+      for (kk = 0; kk < 624 - 397; ++kk) {
+        const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
+      }
+      for (; kk < 623; ++kk) {
+        const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
+      }
+      const uint32_t y = (mt[623] & UPPER) | (mt[0] & LOWER);
+      mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
+      pos = 0;
+    }
+    uint32_t y = mt[pos++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  };
+  int32_t pool[4096];
+  for (int t = 0; t < T; ++t) {
+    for (int i = 0; i < n; ++i) pool[i] = i;
+    for (int i = 0; i < k; ++i) {
+      const uint32_t m = (uint32_t)(n - i);
+      int bits = 0;
+      for (uint32_t v = m; v; v >>= 1) ++bits;
+      uint32_t r;
+      do { r = next_u32() >> (32 - bits); } while (r >= m);
+      out_idx[t * k + i] = pool[r];
+      pool[r] = pool[n - i - 1];
+    }
+  }
+  *mti = pos;
+  return 0;
+}
 }  // extern "C"

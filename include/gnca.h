@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GNCA_VERSION 103
+#define GNCA_VERSION 104
 
 #define GNCA_ERR_ARG (-1)         /* null pointer / bad size */
 #define GNCA_ERR_UNSUPPORTED (-2) /* shape or flag combination without a kernel */
@@ -187,6 +187,14 @@ int gnca_rollout_bwd_bptt(const gnca_model* m, const float* packed_dev, int B, i
                           const gnca_schedule* sched, void* bptt_dev, size_t bptt_bytes, const float* gT_dev,
                           float* g0_dev, float* gparams_dev, void* workspace_dev, size_t workspace_bytes,
                           void* stream);
+
+/*
+ * HOST function (no device work): T consecutive `random.sample(range(n), k)` draws of CPython's `random` module on
+ * its own MT19937 state (`mt[624]`, `*mti` = random.getstate()[1][:624], [624]); state advanced in place so the caller
+ * can `random.setstate` it back -- the python RNG stream stays exactly what T reference `forward` calls consume
+ * (graph_augmentation.py:120-121).  out_idx: [T][k] indices into the offset table.
+ */
+int gnca_host_sample_indices(uint32_t* mt, int32_t* mti, int n, int k, int T, int32_t* out_idx);
 
 /* ------------------------------------------------------------------ training glue ----------- */
 /* per_sample[b] = mean_{4HW}([rgb*a, a] - target)^2 ; gx (optional) = d(scale * sum_b per_sample[b])/dx, [B,C,H,W] */

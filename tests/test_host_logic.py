@@ -124,3 +124,20 @@ def test_pool_semantics():
     assert torch.equal(pool.pool[idx[1]], batch[1])
     s = make_seed(16, 8, 2)
     assert float(s.sum()) == 26.0 and float(s[:, :3].abs().sum()) == 0.0
+
+
+def test_native_offset_sampling_is_the_python_stream():
+    """gnca_host_sample_indices (C, MT19937 replay) == T x random.sample(graph.offsets, k), state included."""
+    import random
+    import graph_neural_cellular_automata_b200 as G
+    from graph_neural_cellular_automata_b200.modules import graph_augmentation as GA
+    m = G.NeuralCAGraph(16, update_hidden=128, img_size=40, graph_zero_padded_shift=False)
+    assert GA._native_sample_ok(len(m.graph.offsets), 8)
+    for seed, T in ((0, 4), (7, 96), (123, 400)):
+        random.seed(seed)
+        ref = [random.sample(m.graph.offsets, 8) for _ in range(T)]
+        after = random.getstate()
+        random.seed(seed)
+        arr = m.graph.draw_offsets_array(T)
+        assert random.getstate() == after                       # the stream continues exactly where T forwards leave it
+        assert [[tuple(int(v) for v in o) for o in st] for st in arr] == [[tuple(o) for o in st] for st in ref]
