@@ -153,3 +153,21 @@ def test_inference_does_not_allocate_history():
         rollout(m, x0, s, impl="resident")
     torch.cuda.synchronize()
     assert torch.cuda.max_memory_allocated() - base < 64 << 20
+
+
+def test_resident_fwd_bwd_is_bitwise_deterministic():
+    """No atomics, fixed reduction orders, fixed slot order: repeated runs must agree bit for bit (a race between the
+    CTAs of a cluster or between warps would show up here as run-to-run noise)."""
+    m = graph_model(True)
+    B, T = 8, 14
+    x0 = _grown_state(m, B, 40, 40, steps=30, seed=3)
+    s = _sched(m, B, 40, 40, T, seed=21)
+    ref = None
+    for rep in range(4):
+        out = _run(m, x0, s, "resident")
+        flat = [out[0], out[1], out[2]] + [g for g in out[3].values() if g is not None]
+        if ref is None:
+            ref = flat
+        else:
+            for a, b in zip(ref, flat):
+                assert torch.equal(a, b), rep
