@@ -285,8 +285,20 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
         xT_host.copy_(xT, non_blocking=True)
         torch.cuda.synchronize()
 
-    for i in range(3):
+    if os.environ.get("GNCA_E2E_DEBUG"):
+        import time as _t
+        for i in range(5):
+            t_a = _t.perf_counter(); x0_ = x0_host.to(dev, non_blocking=True); t_b = _t.perf_counter()
+            sc_ = new_schedule(7000 + i); t_c = _t.perf_counter(); y_ = one_rollout(x0_, sc_); t_d = _t.perf_counter()
+            xT_host.copy_(y_, non_blocking=True); t_e = _t.perf_counter(); torch.cuda.synchronize(); t_f = _t.perf_counter()
+            print("[e2e debug] h2d %.3f sched %.3f launch %.3f d2h-call %.3f sync %.3f total %.3f ms" % (
+                (t_b - t_a) * 1e3, (t_c - t_b) * 1e3, (t_d - t_c) * 1e3, (t_e - t_d) * 1e3, (t_f - t_e) * 1e3, (t_f - t_a) * 1e3),
+                file=sys.stderr)
+    import gc
+    for i in range(8):
         e2e_once(5000 + i)
+    gc.collect()
+    gc.freeze()          # the timed loop allocates a handful of small objects per call; do not rescan the rest of the heap
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(kWT, 2) k_rep_wgrad(WgradArgs A) {
       __syncthreads();                                   // this batch has landed
       const float* raw = RAW + buf * RAWR;
       const float* rh = RH + buf * RAWH;
-#pragma unroll 2
+#pragma unroll 4
       for (int cl = 0; cl < nb; ++cl) {
         const float* rc = raw + cl * kRecStride;
         const float4 g = *reinterpret_cast<const float4*>(rh + cl * kHghStride + HID + 4 * jg);
