@@ -619,24 +619,30 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
       }
     }
     REP_MARK(9);
-    {
-      const int nf = (t + 1 < R.T) ? n_fire_tasks : 0, ntask = nf + n_hist_tasks;
+    // Side jobs of the step, statically spread over warps 1..15 (warp 0 runs the GroupNorm exchange).  The BPTT history
+    // of x_t must be stored BEFORE my partial goes out (that message tells the peers they may overwrite x_t here); the
+    // fire bits of step t+1 touch no state, so a warp that had a tile generates them in the shadow of the exchange.
+    auto side_jobs = [&](const bool fire, const bool hist) {
+      const int nf = (t + 1 < R.T) ? n_fire_tasks : 0;
       float* hdst = R.hist ? R.hist + (size_t)t * a.B * C * HW + sample_off : nullptr;
-      // static assignment (warps 15, 14, ... first: with few cells those have no tile); a shared work counter costs an
-      // atomic round trip per task on the critical path of whichever warp finishes its tiles first
+      if (fire) {
 #pragma unroll 1
-      for (int task = kPW - 1 - warp; task < ntask; task += kPW) {
-        if (task < nf) {
-          fire_task(task, t + 1, cur ^ 1, sparse_fire && t >= 1);
-        } else {
+        for (int task = kPW - 1 - warp; task < nf; task += kPW - 1) fire_task(task, t + 1, cur ^ 1, sparse_fire && t >= 1);
+      }
+      if (hist) {
+#pragma unroll 1
+        for (int task = warp - 1; task < n_hist_tasks; task += kPW - 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int i = (task - nf) * 256 + j * 32 + lane;
+            const int i = task * 256 + j * 32 + lane;
             if (i < hist_items) store_item(hdst, my_lo, my_hi, i);
           }
         }
       }
-    }
+    };
+    const bool had_tile = n_my <= 32 ? (2 * warp < n_my) : n_my <= 64 ? (4 * warp < n_my) : (((n_my * warp) >> 4) < ((n_my * (warp + 1)) >> 4));
+    const bool fire_early = !use_async || !had_tile;
+    if (warp > 0) side_jobs(fire_early, true);
     REP_MARK(1);
 
     // ---- GroupNorm(1,C) partials (ncagraph.py:153): warp -> block -> every CTA of the cluster -------------------
@@ -679,6 +685,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
       REP_MARK(2);
       sched_commit(cur);
       sched_fetch(t + 3);
+      if (warp > 0 && !fire_early) side_jobs(true, false);
       if (warp == 0) mbar_wait(mbarA, (uint32_t)(t & 1));
     }
     REP_MARK(3);
@@ -705,6 +712,34 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     if (use_async && tid == 32) mbar_expect_tx(mbarB, (uint32_t)(nact - n_my) * (uint32_t)(C * 4));
     __syncthreads();
     REP_MARK(10);
+    // (my active cells first: the pushes travel to the peers while everybody runs its local idle pass)
+    {
+      // my active cells: x + gain * tanh(gn(u)); written into every replica (alpha: pre-gate plane)
+      const float sc = s_aff[0][c], bi = s_aff[1][c];
+#pragma unroll 1
+      for (int slot = warp * CPL + hwi; slot < n_my; slot += kPW * CPL) {
+        {
+          const unsigned ent = s_list[slot];
+          const int cell = (int)(ent >> 8) * W + (int)(ent & 255u);
+          const float u = slot < R.ucap ? sU[slot * C + c] : over[(size_t)(slot - R.ucap) * C + c];
+          const float d = tanhf(fmaf(u, sc, bi)) * a.update_gain;
+          float* loc = (c == 3) ? (sAt + cell) : (sX + cell * C + c);
+          const float v = ((c == 3) ? sAg[cell] : *loc) + d;
+          *loc = v;
+          const uint32_t la = smem_u32(loc);
+          if (use_async) {
+#pragma unroll
+            for (int pr = 0; pr < 7; ++pr)
+              if (pr + 1 < NC) st_async_f32(la + pd[pr], v, mbarB + pd[pr]);
+          } else {
+#pragma unroll
+            for (int pr = 0; pr < 7; ++pr)
+              if (pr + 1 < NC) st_cluster_f32(la + pd[pr], v);
+          }
+        }
+      }
+    }
+    REP_MARK(12);
     {
       // inactive cells: x_c += idle_c (their masked pre-norm update is 0, ncagraph.py:149-155); float4 per (cell, quad)
       const float4 i4 = *reinterpret_cast<const float4*>(&s_aff[2][4 * (tid & 3)]);
@@ -740,33 +775,6 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
           if (!(nib & 2u)) sAt[4 * q + 1] = ag.y + idle3;
           if (!(nib & 4u)) sAt[4 * q + 2] = ag.z + idle3;
           if (!(nib & 8u)) sAt[4 * q + 3] = ag.w + idle3;
-        }
-      }
-    }
-    REP_MARK(12);
-    {
-      // my active cells: x + gain * tanh(gn(u)); written into every replica (alpha: pre-gate plane)
-      const float sc = s_aff[0][c], bi = s_aff[1][c];
-#pragma unroll 1
-      for (int slot = warp * CPL + hwi; slot < n_my; slot += kPW * CPL) {
-        {
-          const unsigned ent = s_list[slot];
-          const int cell = (int)(ent >> 8) * W + (int)(ent & 255u);
-          const float u = slot < R.ucap ? sU[slot * C + c] : over[(size_t)(slot - R.ucap) * C + c];
-          const float d = tanhf(fmaf(u, sc, bi)) * a.update_gain;
-          float* loc = (c == 3) ? (sAt + cell) : (sX + cell * C + c);
-          const float v = ((c == 3) ? sAg[cell] : *loc) + d;
-          *loc = v;
-          const uint32_t la = smem_u32(loc);
-          if (use_async) {
-#pragma unroll
-            for (int pr = 0; pr < 7; ++pr)
-              if (pr + 1 < NC) st_async_f32(la + pd[pr], v, mbarB + pd[pr]);
-          } else {
-#pragma unroll
-            for (int pr = 0; pr < 7; ++pr)
-              if (pr + 1 < NC) st_cluster_f32(la + pd[pr], v);
-          }
         }
       }
     }
@@ -927,8 +935,8 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
     unsigned long long h[16];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    const char* names[13] = {"top", "S2 side jobs", "stats push", "wait A", "S3 active+push", "wait B",
-                             "S4 gate + S1 list", "-", "(sum n_my)", "S2 tiles(warp0)", "S3 finalize+sync", "S3 idle x", "S3 idle alpha"};
+    const char* names[13] = {"top", "S2 side jobs", "stats push", "wait A", "S3 idle alpha", "wait B",
+                             "S4 gate + S1 list", "-", "(sum n_my)", "S2 tiles(warp0)", "S3 finalize+sync", "S3 idle x", "S3 active+push"};
     fprintf(stderr, "[gnca rep phase cycles, CTA%d, T=%d]", R.dbg_cta, R.T);
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
     fprintf(stderr, "\n");
