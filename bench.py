@@ -12,7 +12,8 @@ growth from the single-cell seed.  A "step" of this bench = ONE such rollout (B*
   cpu_baseline  : oracle/ port of the reference's PyTorch path on the host cores (N=1, rank 0).
   --impl reference : the oracle port alone, same JSON shape.
 
-Other workloads for development: --workload c3 (training step fwd+bwd, B=32), c5s (256x256x32 scale-up slice).
+Other workloads: --workload c3 (training step fwd+bwd, B=32, T=64: also part of the default line as `fwd_bwd`),
+c3l (the same at T=300, long regime), c5s (256x256x32 scale-up slice, streaming kernels).
 """
 from __future__ import annotations
 
@@ -51,6 +52,9 @@ def workload_cfg(name):
                     fire_rate=0.5, message_every=1, train=False, flop=FLOP_FWD_GRAPH_S)
     if name == "c3":
         return dict(name="c3: graph NCA training step (fwd+bwd, short regime)", C=16, H=40, W=40, B=32, T=64,
+                    hidden=128, fire_rate=0.7, message_every=3, train=True, flop=FLOP_FWDBWD_GRAPH_S)
+    if name == "c3l":
+        return dict(name="c3l: graph NCA training step (fwd+bwd, long regime)", C=16, H=40, W=40, B=32, T=300,
                     hidden=128, fire_rate=0.7, message_every=3, train=True, flop=FLOP_FWDBWD_GRAPH_S)
     if name == "c5s":
         return dict(name="c5 slice: 256x256x32 fwd rollout", C=32, H=256, W=256, B=16, T=20, hidden=128,
