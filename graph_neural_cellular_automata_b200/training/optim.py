@@ -60,3 +60,44 @@ class FusedNormalizedAdam:
         self.flat.copy_(sd["flat"]); self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.step_count = int(sd["step"]); self.lr = float(sd.get("lr", self.lr))
         self.model.invalidate_packed()
+
+    # ---- torch.optim.Adam-format state (what the reference's checkpoints hold: train...:405-416) -------------------
+    def torch_state_dict(self):
+        """State in `torch.optim.Adam(model.parameters()).state_dict()` format (indices = position in
+        `model.parameters()`), so a checkpoint written here resumes in the reference's trainer and vice versa."""
+        params = list(self.model.parameters())
+        index = {id(p): i for i, p in enumerate(params)}
+        state = {}
+        if self.step_count > 0:
+            for ci, p in enumerate(self.model.canonical_params()):
+                if not isinstance(p, torch.nn.Parameter) or not self.has_grad[ci]:
+                    continue
+                sl = slice(self.seg[ci], self.seg[ci + 1])
+                state[index[id(p)]] = {"step": torch.tensor(float(self.step_count)),
+                                       "exp_avg": self.exp_avg[sl].view(p.shape).clone(),
+                                       "exp_avg_sq": self.exp_avg_sq[sl].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_torch_state_dict(self, sd) -> None:
+        """Inverse of `torch_state_dict`; states of parameters this optimiser does not own (`gate_mlp.*`) are ignored."""
+        params = list(self.model.parameters())
+        index = {id(p): i for i, p in enumerate(params)}
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        self.weight_decay = float(g["weight_decay"])
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+        step = 0
+        for ci, p in enumerate(self.model.canonical_params()):
+            if not isinstance(p, torch.nn.Parameter) or not self.has_grad[ci]:
+                continue
+            st = sd["state"].get(index[id(p)])
+            if st is None:
+                continue
+            sl = slice(self.seg[ci], self.seg[ci + 1])
+            self.exp_avg[sl].copy_(st["exp_avg"].reshape(-1).to(self.exp_avg.device))
+            self.exp_avg_sq[sl].copy_(st["exp_avg_sq"].reshape(-1).to(self.exp_avg.device))
+            step = max(step, int(float(st["step"])))
+        self.step_count = step
