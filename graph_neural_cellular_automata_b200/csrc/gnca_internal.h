@@ -64,6 +64,7 @@ size_t rep_bptt_bytes(const gnca_model& m, int B, int H, int W, int T);     // 0
 void rep_bptt_carve(void* base, int B, int H, int W, int T, float** rec, uint32_t** masks, float** stats,
                     float** hgh = nullptr);
 size_t rep_bwd_workspace_bytes(const gnca_model& m, int B, int H, int W);
+bool rep_bwd_supported(const gnca_model& m, int B, int H, int W, int k);    // a launch configuration of k_rep_bwd exists
 int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,
                 const gnca_schedule& sched, void* bptt, const float* gT, float* g0, float* gparams, void* workspace,
                 cudaStream_t st);

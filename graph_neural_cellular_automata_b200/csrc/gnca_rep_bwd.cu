@@ -793,6 +793,56 @@ size_t rep_bwd_workspace_bytes(const gnca_model& m, int B, int H, int W) {
   return f * sizeof(float) + 1024;
 }
 
+// cluster size / tile size / shared memory of k_rep_bwd for a batch: the largest NC in {8,4,2,1} whose bands start at a
+// quad boundary, that fits shared memory (220 KB dynamic + ~4 KB static) and keeps all B clusters co-resident; else the
+// smallest NC that fits (waves).  Returns false when nothing fits.
+static bool pick_rep_bwd_config(int B, int HW, cudaStream_t st, int* out_nc, int* out_gmax, size_t* out_smem) {
+  const int C = 16;
+  const char* env_nc = getenv("GNCA_RESIDENT_NC");
+  const int cands[4] = {8, 4, 2, 1};
+  int pick = -1, pick_gmax = 8;
+  size_t pick_smem = 0;
+  for (int pass = 0; pass < 2 && pick < 0; ++pass) {
+    for (int ci = (pass == 0 ? 0 : 3); ci >= 0 && ci < 4; ci += (pass == 0 ? 1 : -1)) {
+      const int NC = cands[ci];
+      if (env_nc && atoi(env_nc) != NC) continue;
+      if ((HW % (4 * NC)) != 0) continue;                 // bands start at a quad boundary
+      int gmax = 8;
+      size_t smem = rep_bwd_smem_bytes(C, HW, NC, gmax);
+      if (smem > 220 * 1024) { gmax = 4; smem = rep_bwd_smem_bytes(C, HW, NC, gmax); }
+      if (smem > 220 * 1024) continue;
+      if (cudaFuncSetAttribute(k_rep_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(B * NC); q.blockDim = dim3(kQT); q.dynamicSmemBytes = smem; q.stream = st;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = NC; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, k_rep_bwd<16>, &q) != cudaSuccess || ncl < 1) {
+        cudaGetLastError();
+        continue;
+      }
+      if (pass == 0 && B > ncl && !env_nc) continue;
+      pick = NC; pick_smem = smem; pick_gmax = gmax;
+      break;
+    }
+  }
+  if (pick < 0) return false;
+  *out_nc = pick; *out_gmax = pick_gmax; *out_smem = pick_smem;
+  return true;
+}
+
+bool rep_bwd_supported(const gnca_model& m, int B, int H, int W, int k) {
+  if (rep_bptt_bytes(m, B, H, W, 1) == 0 || k > 16) return false;
+  int nc, gmax;
+  size_t smem;
+  return pick_rep_bwd_config(B, H * W, nullptr, &nc, &gmax, &smem);
+}
+
 int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,
                 const gnca_schedule& sched, void* bptt, const float* gT, float* g0, float* gparams, void* workspace,
                 cudaStream_t st) {
@@ -824,36 +874,9 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
   R.affpart = affpart;
   R.damage = sched.damage; R.damage_step = sched.damage_step;
 
-  const char* env_nc = getenv("GNCA_RESIDENT_NC");
-  const int cands[4] = {8, 4, 2, 1};
   int pick = -1, pick_gmax = 8;
   size_t pick_smem = 0;
-  for (int pass = 0; pass < 2 && pick < 0; ++pass) {
-    for (int ci = (pass == 0 ? 0 : 3); ci >= 0 && ci < 4; ci += (pass == 0 ? 1 : -1)) {
-      const int NC = cands[ci];
-      if (env_nc && atoi(env_nc) != NC) continue;
-      if ((HW % (4 * NC)) != 0) continue;                 // bands start at a quad boundary
-      int gmax = 8;
-      size_t smem = rep_bwd_smem_bytes(C, HW, NC, gmax);
-      if (smem > 226 * 1024) { gmax = 4; smem = rep_bwd_smem_bytes(C, HW, NC, gmax); }
-      if (smem > 226 * 1024) continue;
-      GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cudaLaunchConfig_t q{};
-      q.gridDim = dim3(B * NC); q.blockDim = dim3(kQT); q.dynamicSmemBytes = smem; q.stream = st;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = NC; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-      q.attrs = qa; q.numAttrs = 1;
-      int ncl = 0;
-      if (cudaOccupancyMaxActiveClusters(&ncl, k_rep_bwd<16>, &q) != cudaSuccess || ncl < 1) {
-        cudaGetLastError();
-        continue;
-      }
-      if (pass == 0 && B > ncl && !env_nc) continue;
-      pick = NC; pick_smem = smem; pick_gmax = gmax;
-      break;
-    }
-  }
+  if (!pick_rep_bwd_config(B, HW, st, &pick, &pick_gmax, &pick_smem)) pick = -1;
   if (pick < 0) return GNCA_ERR_UNSUPPORTED;
   R.NC = pick; R.gmax = pick_gmax;
   if (getenv("GNCA_DEBUG")) fprintf(stderr, "[gnca] resident bwd: B=%d NC=%d smem=%zu\n", B, pick, pick_smem);

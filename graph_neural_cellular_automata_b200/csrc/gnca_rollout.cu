@@ -209,6 +209,8 @@ int gnca_rollout_fwd_bptt(const gnca_model* m, const float* packed_dev, int B, i
   RolloutWorkspace r = carve_rollout(workspace_dev, *m, B, H, W);
   if (r.bytes > workspace_bytes) return GNCA_ERR_WORKSPACE;
   const bool graph = (m->flags & GNCA_F_GRAPH) != 0;
+  // the records are only worth writing if the resident backward can consume them for this batch / shape
+  if (!rep_bwd_supported(*m, B, H, W, graph ? sched->k : 0)) return GNCA_ERR_UNSUPPORTED;
   const Packed P = make_packed(m->C, m->hidden, m->d_model, graph);
   float *rec, *stats;
   uint32_t* masks;

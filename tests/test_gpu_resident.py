@@ -171,3 +171,10 @@ def test_resident_fwd_bwd_is_bitwise_deterministic():
         else:
             for a, b in zip(ref, flat):
                 assert torch.equal(a, b), rep
+
+
+def test_batch_larger_than_any_cluster_split():
+    """B = 80 > 74 co-resident 2-CTA clusters: one CTA per sample (NC = 1) in the forward and the backward"""
+    m = graph_model(True)
+    x0 = _grown_state(m, 80, 40, 40, steps=14, seed=4)
+    _compare(m, x0, _sched(m, 80, 40, 40, 3, seed=22))
