@@ -168,10 +168,10 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
   if (tid < HID) { const int l = tid >> 2, jj = tid & 3; sb1[tid] = packed[P.b1 + l + 32 * jj]; }
 #pragma unroll 1
   for (int i = tid; i < HID * C; i += kPT) { const int j = i / C, cc = i - j * C; sW2P[j * kW2S + cc] = packed[P.w2t + i]; }
-  float wm[C];                                               // Wm[c][:] of this lane's channel, bm[c]
+  __shared__ __align__(16) float s_wm[C][C + 4];                // Wm rows (registers are the scarce resource of this kernel)
   float bm_c = 0.f;
 #pragma unroll
-  for (int ci = 0; ci < C; ++ci) wm[ci] = graph ? packed[P.wm + c * C + ci] : 0.f;
+  for (int ci = 0; ci < C; ++ci) if (tid < C) s_wm[tid][ci] = graph ? packed[P.wm + tid * C + ci] : 0.f;
   if (graph) bm_c = packed[P.bm + c];
   const float wuni = k > 0 ? 1.0f / (float)k : 0.f;
   if (tid == 0) { float as = 0.f; for (int n = 0; n <= 16; ++n) { s_astab[n] = as; as += wuni; } }
@@ -364,11 +364,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
   prepare_from_state(0);
 
   // peers: 32-bit shared::cluster address deltas (the distributed shared window is linear per rank)
-  uint32_t pd[7];
   {
-    const uint32_t base = smem_u32(sX);
-#pragma unroll
-    for (int pr = 1; pr < 8; ++pr) pd[pr - 1] = (pr < NC) ? mapa_u32(base, (rank + pr) & (NC - 1)) - base : 0u;
   }
   const uint32_t mbarA = smem_u32(&s_mbar[0]), mbarB = smem_u32(&s_mbar[1]);
   const bool use_async = R.use_async != 0 && NC > 1;
@@ -497,7 +493,13 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
           if (msg_on) {
             float agg = bm_c * asv[r];
 #pragma unroll
-            for (int ci = 0; ci < C; ++ci) agg = fmaf(wm[ci], __shfl_sync(0xffffffffu, xs[r], (lane & 16) | ci), agg);
+            for (int c4 = 0; c4 < C / 4; ++c4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(&s_wm[c][4 * c4]);
+              agg = fmaf(w4.x, __shfl_sync(0xffffffffu, xs[r], (lane & 16) | (4 * c4)), agg);
+              agg = fmaf(w4.y, __shfl_sync(0xffffffffu, xs[r], (lane & 16) | (4 * c4 + 1)), agg);
+              agg = fmaf(w4.z, __shfl_sync(0xffffffffu, xs[r], (lane & 16) | (4 * c4 + 2)), agg);
+              agg = fmaf(w4.w, __shfl_sync(0xffffffffu, xs[r], (lane & 16) | (4 * c4 + 3)), agg);
+            }
             const float th = tanhf(agg);
             if (c >= c_lo) mval = th * gain_m;
             if (R.rec && slot0 + hwi + CPL * r < lim)
@@ -676,9 +678,10 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
 #pragma unroll
         for (int pr = 0; pr < 7; ++pr) {
           if (lane == pr + 1 && pr + 1 < NC) {
-            const uint32_t la = smem_u32(&s_parts[cur][rank][0]) + pd[pr];
-            st_async_f32(la, t1, mbarA + pd[pr]);
-            st_async_f32(la + 4, t2, mbarA + pd[pr]);
+            const int peer = (rank + pr + 1) & (NC - 1);
+            const uint32_t la = mapa_u32(smem_u32(&s_parts[cur][rank][0]), peer), lm = mapa_u32(mbarA, peer);
+            st_async_f32(la, t1, lm);
+            st_async_f32(la + 4, t2, lm);
           }
         }
       }
@@ -730,11 +733,11 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
           if (use_async) {
 #pragma unroll
             for (int pr = 0; pr < 7; ++pr)
-              if (pr + 1 < NC) st_async_f32(la + pd[pr], v, mbarB + pd[pr]);
+              if (pr + 1 < NC) st_async_f32(mapa_u32(la, (rank + pr + 1) & (NC - 1)), v, mapa_u32(mbarB, (rank + pr + 1) & (NC - 1)));
           } else {
 #pragma unroll
             for (int pr = 0; pr < 7; ++pr)
-              if (pr + 1 < NC) st_cluster_f32(la + pd[pr], v);
+              if (pr + 1 < NC) st_cluster_f32(mapa_u32(la, (rank + pr + 1) & (NC - 1)), v);
           }
         }
       }
