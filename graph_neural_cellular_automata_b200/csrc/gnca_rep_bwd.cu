@@ -129,9 +129,9 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   if (tid < HID) { const int l = tid >> 2, jj = tid & 3; sb1[tid] = packed[P.b1 + l + 32 * jj]; }
 #pragma unroll 1
   for (int i = tid; i < HID * C; i += kQT) { const int j = i / C, cc = i - j * C; sW2P[j * kQW2S + cc] = packed[P.w2t + i]; }
-  float wmT[C];                                              // Wm[cc][c]: column of this lane's INPUT channel
+  __shared__ __align__(16) float s_wmT[C][C + 4];               // s_wmT[c][cc] = Wm[cc][c] (kept out of the registers)
 #pragma unroll
-  for (int cc = 0; cc < C; ++cc) wmT[cc] = graph ? packed[P.wm + cc * C + c] : 0.f;
+  for (int cc = 0; cc < C; ++cc) if (tid < C) s_wmT[tid][cc] = graph ? packed[P.wm + cc * C + tid] : 0.f;
   const float gam_c = gn ? packed[P.gamma + c] : 1.f, bet_c = gn ? packed[P.beta + c] : 0.f;
 
   const size_t sample_off = (size_t)b * C * HW;
@@ -349,7 +349,13 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         float acc = 0.f;                                                     // g_xs[c] = sum_cc Wm[cc][c] gm[cc]
         if (msg_on) {
 #pragma unroll
-          for (int cc = 0; cc < C; ++cc) acc = fmaf(wmT[cc], __shfl_sync(0xffffffffu, gm, (lane & 16) | cc), acc);
+          for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&s_wmT[c][4 * c4]);
+            acc = fmaf(w4.x, __shfl_sync(0xffffffffu, gm, (lane & 16) | (4 * c4)), acc);
+            acc = fmaf(w4.y, __shfl_sync(0xffffffffu, gm, (lane & 16) | (4 * c4 + 1)), acc);
+            acc = fmaf(w4.z, __shfl_sync(0xffffffffu, gm, (lane & 16) | (4 * c4 + 2)), acc);
+            acc = fmaf(w4.w, __shfl_sync(0xffffffffu, gm, (lane & 16) | (4 * c4 + 3)), acc);
+          }
         }
         gxs[r] = acc;
       }
