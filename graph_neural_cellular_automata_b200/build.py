@@ -32,6 +32,8 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
+    # GNCA_PHASE_COUNTERS=1 in the environment compiles the per-phase cycle counters into the resident kernels
+    # (read back with GNCA_PHASE_TIMING=<cta> at run time); off by default: they cost registers in the step loops.
     """Compile every CUDA source for sm_100a into lib/libgnca.so (objects in parallel, then one link)."""
     if not force and not _stale():
         return LIB
@@ -44,7 +46,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
             continue
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", path, "-o", obj]
+        extra = ["-DGNCA_PHASE_COUNTERS"] if os.environ.get("GNCA_PHASE_COUNTERS") else []
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", path, "-o", obj]
         if verbose:
             print("[gnca build]", " ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -56,6 +56,7 @@ struct RepArgs {
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 
+#ifdef GNCA_PHASE_COUNTERS          /* build with -DGNCA_PHASE_COUNTERS for the per-phase cycle counters */
 #define REP_MARK(idx)                                                               \
   do {                                                                              \
     if (R.dbg && tid == 0) {                                                        \
@@ -64,6 +65,9 @@ __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.a
       t_prev = _n;                                                                  \
     }                                                                               \
   } while (0)
+#else
+#define REP_MARK(idx) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, int rank) {

@@ -58,6 +58,7 @@ struct RepBwdArgs {
   int dbg_cta;
 };
 
+#ifdef GNCA_PHASE_COUNTERS          /* build with -DGNCA_PHASE_COUNTERS for the per-phase cycle counters */
 #define REPB_MARK(idx)                                                              \
   do {                                                                              \
     if (R.dbg && tid == 0) {                                                        \
@@ -66,6 +67,9 @@ struct RepBwdArgs {
       t_prev = _n;                                                                  \
     }                                                                               \
   } while (0)
+#else
+#define REPB_MARK(idx) do { } while (0)
+#endif
 
 __device__ __forceinline__ void cl_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
