@@ -39,7 +39,7 @@ FLOP_FWDBWD_GRAPH_S = 53.6e3
 FLOP_FWD_GRAPH_L = 36.7e3
 FP32_LANES = 148 * 128 * 2           # FMA lanes x 2 flop
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_DRAM_BYTES = {("c2", "k_rep_fwd"): 1096704}     # profiles/r01_rep_fwd_summary.md: 1.096704 MB read, 0 written (x_T still in L2)
+NCU_DRAM_BYTES = {("c2", "k_rep_fwd"): 1090304}     # profiles/r01_rep_fwd_summary.md: 1.090304 MB read, 0 written (x_T still in L2)
 
 
 def load_weights(name):

@@ -173,10 +173,10 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
 #pragma unroll 1
   for (int i = tid; i < HID * C; i += kPT) { const int j = i / C, cc = i - j * C; sW2P[j * kW2S + cc] = packed[P.w2t + i]; }
   __shared__ __align__(16) float s_wm[C][C + 4];                // Wm rows (registers are the scarce resource of this kernel)
-  float bm_c = 0.f;
+  __shared__ float s_gbb[3][C];                                  // gamma, beta, bm (registers are scarce)
 #pragma unroll
   for (int ci = 0; ci < C; ++ci) if (tid < C) s_wm[tid][ci] = graph ? packed[P.wm + tid * C + ci] : 0.f;
-  if (graph) bm_c = packed[P.bm + c];
+  if (tid < C) { s_gbb[0][tid] = packed[P.gamma + tid]; s_gbb[1][tid] = packed[P.beta + tid]; s_gbb[2][tid] = graph ? packed[P.bm + tid] : 0.f; }
   const float wuni = k > 0 ? 1.0f / (float)k : 0.f;
   if (tid == 0) { float as = 0.f; for (int n = 0; n <= 16; ++n) { s_astab[n] = as; as += wuni; } }
   const size_t sample_off = (size_t)b * C * HW;
@@ -383,8 +383,6 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
   long long t_prev = clock64();
   float* myY = sY + warp * (C3 * 8);
   short* myq = sq + warp * (8 * 16);
-  float* over = R.u_over ? R.u_over + (size_t)blockIdx.x * R.over_cap * C : nullptr;
-  const float gam_c = packed[P.gamma + c], bet_c = packed[P.beta + c];
 
   for (int t = 0; t < R.T; ++t) {
     const int cur = t & 1;
@@ -495,7 +493,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
         for (int r = 0; r < MPL; ++r) {
           float mval = 0.f;
           if (msg_on) {
-            float agg = bm_c * asv[r];
+            float agg = s_gbb[2][c] * asv[r];
 #pragma unroll
             for (int c4 = 0; c4 < C / 4; ++c4) {
               const float4 w4 = *reinterpret_cast<const float4*>(&s_wm[c][4 * c4]);
@@ -586,7 +584,8 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
             if (slot < lim) {
               const float u = pv[e] + msg[r];
               if (R.rec) R.rec[(((size_t)t * a.B + b) * HW + (size_t)(lo_my + slot)) * kRecStride + kRecU + c] = u;
-              float* dst = slot < R.ucap ? sU + slot * C + c : over + (size_t)(slot - R.ucap) * C + c;
+              float* dst = slot < R.ucap ? sU + slot * C + c
+                                         : R.u_over + ((size_t)blockIdx.x * R.over_cap + (slot - R.ucap)) * C + c;
               *dst = u;
               if (R.u_hist) {
                 const unsigned ent = s_list[slot];
@@ -706,8 +705,8 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
         const float m_ = t1 * R.inv_n;
         const float var = fmaxf(fmaf(t2, R.inv_n, -m_ * m_), 0.f);
         const float r_ = 1.0f / sqrtf(var + a.gn_eps);
-        sc = r_ * gam_c;                      // lane == c for lanes < C
-        bi = bet_c - m_ * sc;
+        sc = r_ * s_gbb[0][lane];             // lane == c for lanes < C
+        bi = s_gbb[1][lane] - m_ * sc;
         idle = tanhf(bi) * a.update_gain;
         if (lane == 0 && rank == 0 && R.stats_hist) {
           R.stats_hist[((size_t)t * a.B + b) * 2] = m_;
@@ -728,7 +727,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
         {
           const unsigned ent = s_list[slot];
           const int cell = (int)(ent >> 8) * W + (int)(ent & 255u);
-          const float u = slot < R.ucap ? sU[slot * C + c] : over[(size_t)(slot - R.ucap) * C + c];
+          const float u = slot < R.ucap ? sU[slot * C + c] : R.u_over[((size_t)blockIdx.x * R.over_cap + (slot - R.ucap)) * C + c];
           const float d = tanhf(fmaf(u, sc, bi)) * a.update_gain;
           float* loc = (c == 3) ? (sAt + cell) : (sX + cell * C + c);
           const float v = ((c == 3) ? sAg[cell] : *loc) + d;
