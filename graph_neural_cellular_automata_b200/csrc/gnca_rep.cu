@@ -7,11 +7,19 @@
 //   * perception (3x3, zero halo) and the mid-range torus senders are read in place with no halo logic;
 //   * the masks are linear cell bitmaps: max-pool > thr is a 3x3 dilation of (alpha > thr) done with funnel
 //     shifts, compaction is popcount prefix sums, and pre_alive(t+1) == post_alive(t) is reused, not recomputed.
-// Per step:  S1 active rows + balanced list  ->  S2 warp-autonomous tiles (sender table, perception, message,
-// layer 1 in registers, layer 2 as a shuffle reduce-scatter; no block barrier, no hidden layer in smem)
-// (the warps without a tile generate the next step's Philox fire bits and store the BPTT history)
-// -> GroupNorm partials pushed to every CTA  [cluster barrier 1]  ->  S3 idle update of all inactive cells (local) + bounded update of my active
-// cells pushed into all NC replicas through DSMEM  [cluster barrier 2]  ->  S4 post-alive gate from bit rows.
+// Per step (reference semantics: ncagraph.py:106-168):
+//   S2  warp-autonomous tiles of 2/4/8 cells over MY share of the active list: sender table, perception, message,
+//       layer 1 in registers, layer 2 as a shuffle reduce-scatter -- no block barrier, no hidden layer in smem.
+//       Warps without a tile generate the next step's Philox fire bits meanwhile; the BPTT history / records of the
+//       step are stored before the hand-over below.
+//   --  GroupNorm partials: warp -> block -> every CTA of the cluster with st.async, counted (8 bytes per peer) on the
+//       peer's mbarrier A.  A peer's partial arriving also says "that peer has finished reading x_t".
+//   S3  warp 0 finishes the statistics; my active cells get x + gain*tanh(gn(u)) and are pushed as 64-byte lines into
+//       ALL NC replicas with st.async (transaction bytes counted on the destination's mbarrier B); while those
+//       travel every CTA runs its local idle update x += idle_c of all inactive cells.
+//   S4  (after mbarrier B) post-alive gate from the bitmap of the updated alpha, fused with the active bitmap /
+//       balanced list of the next step.
+// No cluster barrier and no MEMBAR.GPU inside the step loop (a barrier-based exchange remains as GNCA_REP_SYNC=barrier).
 // HBM is touched at x_0 / x_T and by the optional BPTT history (x_t, u_t of the active cells, statistics).
 #include <cooperative_groups.h>
 #include <cstdio>
@@ -49,7 +57,7 @@ struct RepArgs {
   int damage_step;
   unsigned long long* dbg;
   int dbg_cta;
-  int dbg_repeat;             // development: bit0 = run the S4+S1 block twice (idempotent), bit1 = S3 idle pass twice... 
+  int dbg_repeat;             // development (GNCA_REPEAT): bit0 = run the S4+S1 block twice (idempotent; cost = time delta)
   int use_async;              // 1: st.async + mbarrier transaction counts between the CTAs, 0: two cluster barriers per step
 };
 
