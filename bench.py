@@ -12,7 +12,8 @@ growth from the single-cell seed.  A "step" of this bench = ONE such rollout (B*
   cpu_baseline  : oracle/ port of the reference's PyTorch path on the host cores (N=1, rank 0).
   --impl reference : the oracle port alone, same JSON shape.
 
-Other workloads: --workload c3 (training step fwd+bwd, B=32, T=64: also part of the default line as `fwd_bwd`),
+Other workloads: --workload c1 (classic NCA rollout), c3 (training step fwd+bwd, B=32, T=64: also part of the default
+line as `fwd_bwd`), c4 (c3 with an in-kernel damage mask),
 c3l (the same at T=300, long regime), c5s (256x256x32 scale-up slice, streaming kernels).
 """
 from __future__ import annotations
@@ -53,6 +54,14 @@ def workload_cfg(name):
     if name == "c3":
         return dict(name="c3: graph NCA training step (fwd+bwd, short regime)", C=16, H=40, W=40, B=32, T=64,
                     hidden=128, fire_rate=0.7, message_every=3, train=True, flop=FLOP_FWDBWD_GRAPH_S)
+    if name == "c1":
+        return dict(name="c1: classic NCA fwd rollout, seed growth (the reference's CPU-runnable case, here on the GPU)",
+                    C=16, H=40, W=40, B=8, T=96, hidden=128, fire_rate=0.5, message_every=1, train=False,
+                    flop=17.0e3, classic=True)
+    if name == "c4":
+        return dict(name="c4: graph NCA training step with damage (fwd+bwd, short regime, damaged batch)", C=16, H=40, W=40,
+                    B=32, T=64, hidden=128, fire_rate=0.7, message_every=3, train=True, flop=FLOP_FWDBWD_GRAPH_S,
+                    damage=True)
     if name == "c3l":
         return dict(name="c3l: graph NCA training step (fwd+bwd, long regime)", C=16, H=40, W=40, B=32, T=300,
                     hidden=128, fire_rate=0.7, message_every=3, train=True, flop=FLOP_FWDBWD_GRAPH_S)
@@ -191,9 +200,16 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
     lib = _lib.load()
     C_, H, W, B, T = cfg["C"], cfg["H"], cfg["W"], cfg["B"], cfg["T"]
     torch.manual_seed(42 + rank); random.seed(42 + rank)
-    model = G.NeuralCAGraph(C_, update_hidden=cfg["hidden"], img_size=H, update_gain=0.05, alpha_thr=0.12,
-                            message_gain=0.25, hidden_only=True, graph_zero_padded_shift=False)
-    if C_ == 16:
+    if cfg.get("classic"):
+        model = G.NeuralCA(C_, update_hidden=cfg["hidden"], img_size=H, update_gain=0.05, alpha_thr=0.12)
+        model.load_state_dict(load_weights("weights_classic_ep990.npz"), strict=False)
+        data = "synthetic (seed growth; trained classic 40x40 gecko weights shipped as a fixture)"
+    else:
+        model = G.NeuralCAGraph(C_, update_hidden=cfg["hidden"], img_size=H, update_gain=0.05, alpha_thr=0.12,
+                                message_gain=0.25, hidden_only=True, graph_zero_padded_shift=False)
+    if cfg.get("classic"):
+        pass
+    elif C_ == 16:
         model.load_state_dict(load_weights("weights_graph_ep960.npz"), strict=False)
         data = "synthetic (seed growth; trained 40x40 gecko weights shipped as a fixture)"
     else:
@@ -244,9 +260,14 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
         with torch.no_grad():
             return rollout(model, x0, sched, impl=args.rollout_impl)
 
+    dmg = None
+    if cfg.get("damage"):      # one damage kind / size for the batch, per-sample positions (utils/damage.py), applied in-kernel at step 0
+        from graph_neural_cellular_automata_b200.utils.damage import circle_mask
+        dmg = circle_mask(x0_dev, 5).expand_as(x0_dev).contiguous()
+
     def new_schedule(seed):
         return make_schedule(model, B, H, W, T, fire_rate=cfg["fire_rate"], message_every=cfg["message_every"],
-                             fire="philox", seed=seed)
+                             fire="philox", seed=seed, damage=dmg, damage_step=0)
 
     # ---------------- device-resident timing (value) ----------------
     scheds = [new_schedule(1000 + i) for i in range(warmup + steps)]
@@ -410,7 +431,7 @@ def main():
                  "kernels": (r3["roofline"] or {}).get("kernels")}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not cfg["train"]:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not cfg["train"] and not cfg.get("classic"):
         cpu = time_cpu_port(cfg)
 
     if rank == 0:
