@@ -292,4 +292,34 @@ int gnca_host_sample_indices(uint32_t* mt, int32_t* mti, int n, int k, int T, in
   *mti = pos;
   return 0;
 }
+
+// The same draws from a block of raw MT19937 outputs the caller pulled with random.getrandbits(32 * n_words): no
+// state conversion on the python side (getstate -> numpy -> setstate costs more than the sampling).  Writes the
+// chosen offsets straight from the table; *used = words consumed (the caller restores the state and skips exactly
+// that many outputs).  Returns GNCA_ERR_UNSUPPORTED when the block is too short (the caller retries with more).
+int gnca_host_sample_offsets_words(const uint32_t* words, int n_words, const int8_t* table /*[n][2]*/, int n, int k,
+                                   int T, int8_t* out_off /*[T][k][2]*/, int32_t* used) {
+  if (!words || !table || !out_off || !used || n <= 0 || k < 0 || k > n || n > 4096 || T < 0) return GNCA_ERR_ARG;
+  int pos = 0;
+  int32_t pool[4096];
+  for (int t = 0; t < T; ++t) {
+    for (int i = 0; i < n; ++i) pool[i] = i;
+    for (int i = 0; i < k; ++i) {
+      const uint32_t m = (uint32_t)(n - i);
+      int bits = 0;
+      for (uint32_t v = m; v; v >>= 1) ++bits;
+      uint32_t r;
+      do {
+        if (pos >= n_words) return GNCA_ERR_UNSUPPORTED;
+        r = words[pos++] >> (32 - bits);
+      } while (r >= m);
+      const int src = pool[r];
+      out_off[((size_t)t * k + i) * 2] = table[2 * src];
+      out_off[((size_t)t * k + i) * 2 + 1] = table[2 * src + 1];
+      pool[r] = pool[n - i - 1];
+    }
+  }
+  *used = pos;
+  return 0;
+}
 }  // extern "C"

@@ -45,7 +45,58 @@ def _native_sample(n: int, k: int, T: int):
     return out
 
 
+def _words_sample(table, n: int, k: int, T: int):
+    """T x random.sample(offsets, k) as an int8 [T,k,2] array: a block of raw MT19937 outputs is pulled with ONE
+    random.getrandbits call, the C host function gnca_host_sample_offsets_words replays random.sample on it and says
+    how many outputs it consumed; the saved state is restored and exactly that many outputs are skipped.  Same
+    stream as T reference forwards, no state <-> numpy conversion (that cost more than the sampling itself)."""
+    import ctypes as C
+    import numpy as np
+    from .. import _lib
+    lib = _lib.load()
+    state = random.getstate()
+    out = np.empty((T, k, 2), dtype=np.int8)
+    used = C.c_int32(0)
+    m = int(2.3 * T * k) + 64                      # ~2 outputs per draw at worst (rejection), + margin
+    while True:
+        words = random.getrandbits(32 * m).to_bytes(4 * m, "little")
+        rc = lib.gnca_host_sample_offsets_words(words, m, table.ctypes.data, n, k, T, out.ctypes.data, C.byref(used))
+        random.setstate(state)
+        if rc == 0:
+            break
+        if rc != _lib.GNCA_ERR_UNSUPPORTED or m > (1 << 24):
+            raise RuntimeError("gnca_host_sample_offsets_words failed")
+        m *= 4                                    # block too short (rejection sampling ran long): retry with more
+    if used.value:
+        random.getrandbits(32 * used.value)
+    return out
+
+
 _NATIVE_SAMPLE_CACHE = {}
+_WORDS_SAMPLE_CACHE = {}
+
+
+def _words_sample_ok(offsets, n: int, k: int) -> bool:
+    """One-time self-check per (n, k): the block replay must reproduce random.sample AND leave the same state."""
+    import numpy as np
+    key = (n, k)
+    if key not in _WORDS_SAMPLE_CACHE:
+        ok = False
+        state = random.getstate()
+        try:
+            if state[0] == 3 and len(state[1]) == 625:
+                ref = [[list(o) for o in random.sample(offsets, k)] for _ in range(5)]
+                after_ref = random.getstate()
+                random.setstate(state)
+                table = np.ascontiguousarray(np.asarray(offsets, dtype=np.int8).reshape(n, 2))
+                mine = _words_sample(table, n, k, 5).tolist()
+                ok = mine == ref and random.getstate() == after_ref
+        except Exception:
+            ok = False
+        finally:
+            random.setstate(state)
+        _WORDS_SAMPLE_CACHE[key] = ok
+    return _WORDS_SAMPLE_CACHE[key]
 
 
 def _native_sample_ok(n: int, k: int) -> bool:
@@ -135,9 +186,13 @@ class GraphAugmentation(nn.Module):
         `random.sample` guards the private-API assumption and falls back to plain `random.sample` if it fails."""
         import numpy as np
         n, k = len(self.offsets), min(self.num_neighbors, len(self.offsets))
-        table = np.asarray(self.offsets, dtype=np.int8).reshape(n, 2)
+        table = getattr(self, "_offset_table", None)
+        if table is None or table.shape[0] != n:
+            table = self._offset_table = np.ascontiguousarray(np.asarray(self.offsets, dtype=np.int8).reshape(n, 2))
         if k == 0 or T == 0:
             return np.zeros((T, 0, 2), np.int8)
+        if T >= 4 and _words_sample_ok(self.offsets, n, k):
+            return _words_sample(table, n, k, T)
         if T >= 4 and _native_sample_ok(n, k):
             idx = _native_sample(n, k, T)
         elif _fast_sample_ok(n, k):

@@ -70,6 +70,8 @@ class _PinnedRing:
 
 
 _RING = _PinnedRing()
+_TORCH_DTYPE = {np.dtype(np.float32): torch.float32, np.dtype(np.int8): torch.int8, np.dtype(np.int32): torch.int32,
+                np.dtype(np.uint8): torch.uint8, np.dtype(np.int64): torch.int64}
 
 
 def _upload(arrs: Sequence[np.ndarray], device) -> List[torch.Tensor]:
@@ -87,7 +89,7 @@ def _upload(arrs: Sequence[np.ndarray], device) -> List[torch.Tensor]:
         host = torch.empty(total, dtype=torch.uint8)
     hv = host.numpy()
     for a, off in zip(arrs, offs):
-        hv[off:off + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        hv[off:off + a.nbytes].view(a.dtype)[:] = a.reshape(-1)
     if on_cuda:
         dev = torch.empty(total, dtype=torch.uint8, device=device)
         dev.copy_(host[:total], non_blocking=True)
@@ -96,7 +98,7 @@ def _upload(arrs: Sequence[np.ndarray], device) -> List[torch.Tensor]:
         dev = host[:total].clone()
     out = []
     for a, off in zip(arrs, offs):
-        t = dev[off:off + a.nbytes].view(torch.from_numpy(np.empty(0, a.dtype)).dtype).view(a.shape)
+        t = dev[off:off + a.nbytes].view(_TORCH_DTYPE[a.dtype]).view(a.shape)
         out.append(t)
     return out
 

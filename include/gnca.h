@@ -195,6 +195,14 @@ int gnca_rollout_bwd_bptt(const gnca_model* m, const float* packed_dev, int B, i
  * (graph_augmentation.py:120-121).  out_idx: [T][k] indices into the offset table.
  */
 int gnca_host_sample_indices(uint32_t* mt, int32_t* mti, int n, int k, int T, int32_t* out_idx);
+/*
+ * HOST function: the same T draws taken from `n_words` raw MT19937 outputs (the caller pulled them with
+ * random.getrandbits(32 * n_words), first output = word 0); writes the chosen (dy, dx) pairs of `table` [n][2] to
+ * out_off [T][k][2] and the number of words consumed to *used -- the caller restores the saved state and skips exactly
+ * `used` outputs, so the python stream again equals T reference forward calls.  GNCA_ERR_UNSUPPORTED: block too short.
+ */
+int gnca_host_sample_offsets_words(const uint32_t* words, int n_words, const int8_t* table, int n, int k, int T,
+                                   int8_t* out_off, int32_t* used);
 
 /* ------------------------------------------------------------------ training glue ----------- */
 /* per_sample[b] = mean_{4HW}([rgb*a, a] - target)^2 ; gx (optional) = d(scale * sum_b per_sample[b])/dx, [B,C,H,W] */

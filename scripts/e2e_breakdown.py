@@ -31,3 +31,9 @@ with torch.no_grad():
         t0 = time.perf_counter(); rollout(m, x0, s); return time.perf_counter() - t0
     torch.cuda.synchronize(); ls = [launch_only() for _ in range(20)]; torch.cuda.synchronize()
     print("rollout() host time to return    %.3f ms" % (np.median(ls) * 1e3))
+    import cProfile, pstats
+    for _ in range(20): full()
+    pr = cProfile.Profile(); pr.enable()
+    for _ in range(200): full()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(28)
