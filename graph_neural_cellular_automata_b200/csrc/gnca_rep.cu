@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
   __shared__ float s_astab[17];                               // n * (1/k) summed sequentially (same as the streaming path)
   __shared__ float s_fr[2], s_gain[2];
   __shared__ signed char s_off[2][2 * 16];
-  __shared__ unsigned long long s_dbg[16];
-  if (tid < 16) s_dbg[tid] = 0;
+  __shared__ unsigned long long s_dbg[24];
+  if (tid < 24) s_dbg[tid] = 0;
 
   // ---- weights -> smem ---------------------------------------------------------------------------------------
 #pragma unroll 1
@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
           }
           __syncwarp();
         }
+        REP_MARK(13);
         // 2b: perception (perception.py:9-26, zero halo) + gathered sender state, lane = (cell hwi+2r, channel c)
         float xs[MPL], asv[MPL], msg[MPL];
         const bool isA = (c == 3);
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
             if (c == 0) rc[kRecAs] = as;
           }
         }
+        REP_MARK(14);
         // 2c: message projection + channel policy (ncagraph.py:94-104,141): lane's row of Wm in registers
 #pragma unroll
         for (int r = 0; r < MPL; ++r) {
@@ -518,6 +520,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
           msg[r] = mval;
         }
         __syncwarp();
+        REP_MARK(15);
         // 2d: layer 1, lane = 4 hidden units (permuted), G cells: broadcast y, per-lane w
         float acc[G][4];
         {
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
             }
           }
         }
+        REP_MARK(16);
         // 2e: layer 2: per-lane partial over its 4 hidden units, then a shuffle reduce-scatter that leaves
         //     (cell hwi+2e of the half, channel c) in this lane -- the same ownership as the message.
         constexpr int GB = G < 4 ? G : 4;                  // cells per reduce-scatter block
@@ -605,6 +609,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
           }
         }
         __syncwarp();
+        REP_MARK(17);
       }
     };
     // tile size: as many warps as possible get a tile (latency), larger tiles amortise the weight reads (throughput)
@@ -834,7 +839,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
   __syncthreads();
   if (R.hist) store_state(R.hist + (size_t)R.T * a.B * C * HW + sample_off, my_lo, my_hi);
   store_state(R.xT + sample_off, my_lo, my_hi);
-  if (R.dbg && blockIdx.x == R.dbg_cta && tid < 16) R.dbg[tid] = s_dbg[tid];
+  if (R.dbg && blockIdx.x == R.dbg_cta && tid < 24) R.dbg[tid] = s_dbg[tid];
   cl_arrive(); cl_wait();      // nobody exits while a peer may still address its shared memory
 }
 
@@ -935,8 +940,8 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
             R.ucap, R.over_cap, pick_smem, pick_ncl);
   static unsigned long long* dbg_buf = nullptr;
   if (getenv("GNCA_PHASE_TIMING")) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
-    cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), st);
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 24 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbg_buf, 0, 24 * sizeof(unsigned long long), st);
     R.dbg = dbg_buf;
     R.dbg_cta = atoi(getenv("GNCA_PHASE_TIMING"));
   }
@@ -946,13 +951,14 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
   if (e != cudaSuccess) return (int)e;
   GNCA_LAUNCH_CHECK();
   if (R.dbg) {
-    unsigned long long h[16];
+    unsigned long long h[24];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    const char* names[13] = {"top", "S2 side jobs", "stats push", "wait A", "S3 idle alpha", "wait B",
-                             "S4 gate + S1 list", "-", "(sum n_my)", "S2 tiles(warp0)", "S3 finalize+sync", "S3 idle x", "S3 active+push"};
+    const char* names[18] = {"top", "S2 side jobs", "stats push", "wait A", "S3 idle alpha", "wait B",
+                             "S4 gate + S1 list", "-", "(sum n_my)", "S2 tiles rest(warp0)", "S3 finalize+sync", "S3 idle x", "S3 active+push",
+                             "tile: sender table", "tile: perception+gather", "tile: message", "tile: layer 1", "tile: layer 2 + RS"};
     fprintf(stderr, "[gnca rep phase cycles, CTA%d, T=%d]", R.dbg_cta, R.T);
-    for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
+    for (int i = 0; i < 18; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
     fprintf(stderr, "\n");
   }
   return 0;
