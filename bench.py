@@ -14,7 +14,8 @@ growth from the single-cell seed.  A "step" of this bench = ONE such rollout (B*
 
 Other workloads: --workload c1 (classic NCA rollout), c3 (training step fwd+bwd, B=32, T=64: also part of the default
 line as `fwd_bwd`), c4 (c3 with an in-kernel damage mask),
-c3l (the same at T=300, long regime), c5s (256x256x32 scale-up slice, streaming kernels).
+c3l (the same at T=300, long regime), c5s (256x256x32 scale-up slice, streaming kernels), c5 (the full per-GPU share of
+BASELINE configs[4]: B=128, T=1000, damage at t=500 -- seconds per rollout: run it with --steps 2 --warmup 1).
 """
 from __future__ import annotations
 
@@ -68,6 +69,10 @@ def workload_cfg(name):
     if name == "c5s":
         return dict(name="c5 slice: 256x256x32 fwd rollout", C=32, H=256, W=256, B=16, T=20, hidden=128,
                     fire_rate=0.5, message_every=1, train=False, flop=FLOP_FWD_GRAPH_L)
+    if name == "c5":      # BASELINE configs[4] per GPU: batch 1024 over 8 GPUs = 128 per GPU, 1000 steps, damage at t = 500
+        return dict(name="c5: 256x256x32 regeneration rollout, B=128 per GPU, T=1000, circle damage at t=500", C=32, H=256,
+                    W=256, B=128, T=1000, hidden=128, fire_rate=0.5, message_every=1, train=False, flop=FLOP_FWD_GRAPH_L,
+                    damage=True, damage_step=500, damage_size=64)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -263,11 +268,11 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
     dmg = None
     if cfg.get("damage"):      # one damage kind / size for the batch, per-sample positions (utils/damage.py), applied in-kernel at step 0
         from graph_neural_cellular_automata_b200.utils.damage import circle_mask
-        dmg = circle_mask(x0_dev, 5).expand_as(x0_dev).contiguous()
+        dmg = circle_mask(x0_dev, int(cfg.get("damage_size", 5))).expand_as(x0_dev).contiguous()
 
     def new_schedule(seed):
         return make_schedule(model, B, H, W, T, fire_rate=cfg["fire_rate"], message_every=cfg["message_every"],
-                             fire="philox", seed=seed, damage=dmg, damage_step=0)
+                             fire="philox", seed=seed, damage=dmg, damage_step=int(cfg.get("damage_step", 0)))
 
     # ---------------- device-resident timing (value) ----------------
     scheds = [new_schedule(1000 + i) for i in range(warmup + steps)]
@@ -320,7 +325,7 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
                 (t_b - t_a) * 1e3, (t_c - t_b) * 1e3, (t_d - t_c) * 1e3, (t_e - t_d) * 1e3, (t_f - t_e) * 1e3, (t_f - t_a) * 1e3),
                 file=sys.stderr)
     import gc
-    for i in range(8):
+    for i in range(8 if updates < 1e8 else 1):          # second-long rollouts (c5) need no repeated host warm-up
         e2e_once(5000 + i)
     gc.collect()
     gc.freeze()          # the timed loop allocates a handful of small objects per call; do not rescan the rest of the heap
@@ -371,8 +376,9 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
                                    "hbm_gbs 6547.8 measured is far from binding: see hbm_view)",
                     "note": "achieved = DENSE algorithmic flops (every cell counted) / measured kernel time; the kernel "
                             "skips cells whose fire*alive mask is 0, so frac is a dense-equivalent figure",
-                    "hbm_view": {"algorithmic_bytes_per_step": int(2 * x0_host.numel() * 4),
-                                 "achieved_GBps": 2 * x0_host.numel() * 4 * nprof / (ms * 1e-3) / 1e9,
+                    # resident kernel: x_0 in + x_T out per rollout; streaming step kernels: state in + out per CA step
+                    "hbm_view": {"algorithmic_bytes_per_step": int(2 * x0_host.numel() * 4 * (T if kname in ("k_update", "k_apply") else 1)),
+                                 "achieved_GBps": 2 * x0_host.numel() * 4 * (T if kname in ("k_update", "k_apply") else 1) * nprof / (ms * 1e-3) / 1e9,
                                  "peak_GBps": 6547.8},
                     "share_of_step": ms / nprof / (dev_ms_max / steps), "kernels": kernels_ms}
 
