@@ -364,7 +364,11 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
         if per_kernel:
             kname = max(per_kernel, key=lambda k: per_kernel[k][0])
             ms, n = per_kernel[kname]
-            flops_per_launch = cfg["flop"] * updates * nprof / n        # algorithmic (dense) flops / launch
+            # algorithmic (dense) flops / launch.  Training step: the credited 3 x forward flops split evenly over its three
+            # kernels (forward 17.9 k; data gradients gh, gy, perception^T, message^T 17.9 k; weight gradients 17.8 k per
+            # cell-update -- the hidden-layer recompute inside k_rep_bwd is overhead and not credited)
+            kflop = cfg["flop"] / 3.0 if cfg["train"] else cfg["flop"]
+            flops_per_launch = kflop * updates * nprof / n
             avg_s = ms * 1e-3 / n
             clocks = sampler.result()
             mhz = clocks["sm_max_mhz"] or 1965

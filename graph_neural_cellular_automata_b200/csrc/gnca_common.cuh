@@ -235,32 +235,39 @@ __device__ __forceinline__ void perceive(const float* __restrict__ xs /* sample 
 // update MLP forward for P cells per thread: dx = W2 relu(W1 y + b1)   (ncagraph.py:60-65,131)
 // weights are read from shared memory with warp-uniform (broadcast) float4 loads.
 // ------------------------------------------------------------------------------------------------
-template <int C, int P>
+template <int C, int P, int JU = 4>
 __device__ __forceinline__ void mlp_forward(const float (&y)[P][3 * C], float (&dx)[P][C], const float* __restrict__ sW1T,
                                             const float* __restrict__ sb1, const float* __restrict__ sW2T, int hid) {
+  static_assert(JU % 4 == 0, "hidden units per pass: multiples of 4 (float4 weight rows)");
 #pragma unroll
   for (int p = 0; p < P; ++p)
 #pragma unroll
     for (int c = 0; c < C; ++c) dx[p][c] = 0.f;
 #pragma unroll 1
-  for (int j = 0; j < hid; j += 4) {
-    const float4 bb = *reinterpret_cast<const float4*>(sb1 + j);
-    float h[P][4];
+  for (int j = 0; j < hid; j += JU) {        // hid % JU == 0 is checked by the launcher
+    float h[P][JU];
 #pragma unroll
-    for (int p = 0; p < P; ++p) { h[p][0] = bb.x; h[p][1] = bb.y; h[p][2] = bb.z; h[p][3] = bb.w; }
+    for (int q = 0; q < JU / 4; ++q) {
+      const float4 bb = *reinterpret_cast<const float4*>(sb1 + j + 4 * q);
+#pragma unroll
+      for (int p = 0; p < P; ++p) { h[p][4 * q] = bb.x; h[p][4 * q + 1] = bb.y; h[p][4 * q + 2] = bb.z; h[p][4 * q + 3] = bb.w; }
+    }
 #pragma unroll
     for (int k = 0; k < 3 * C; ++k) {
-      const float4 w = *reinterpret_cast<const float4*>(sW1T + k * hid + j);
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        h[p][0] = fmaf(w.x, y[p][k], h[p][0]);
-        h[p][1] = fmaf(w.y, y[p][k], h[p][1]);
-        h[p][2] = fmaf(w.z, y[p][k], h[p][2]);
-        h[p][3] = fmaf(w.w, y[p][k], h[p][3]);
+      for (int q = 0; q < JU / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(sW1T + k * hid + j + 4 * q);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          h[p][4 * q + 0] = fmaf(w.x, y[p][k], h[p][4 * q + 0]);
+          h[p][4 * q + 1] = fmaf(w.y, y[p][k], h[p][4 * q + 1]);
+          h[p][4 * q + 2] = fmaf(w.z, y[p][k], h[p][4 * q + 2]);
+          h[p][4 * q + 3] = fmaf(w.w, y[p][k], h[p][4 * q + 3]);
+        }
       }
     }
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
+    for (int jj = 0; jj < JU; ++jj) {
 #pragma unroll
       for (int p = 0; p < P; ++p) h[p][jj] = fmaxf(h[p][jj], 0.f);
 #pragma unroll

@@ -171,12 +171,96 @@ struct UpdateSmem {
   }
 };
 
-template <int C, int CH>
-__global__ void __launch_bounds__(kThreads) k_update(StepArgs a, Packed P, int hid, const float* __restrict__ packed) {
+// BAL (large problems): the active cells of the whole sample were compacted by k_compact / k_scan into a global list;
+// block j takes the active cells of rank [j*RANGE, (j+1)*RANGE) -- full rounds of NT cells whatever their position.
+// (With per-chunk compaction a chunk of 1024 cells holds ~150-300 active ones: one full round of 256 threads and one
+// nearly empty one, and chunks outside the alive region do nothing; measured 25 % FMA-pipe utilisation at 256x256x32.)
+constexpr int kMaxBalChunks = 1024;
+constexpr int kThreadsBal = 384;
+
+template <int CH>
+__global__ void __launch_bounds__(kThreads) k_compact(StepArgs a, int C, uint16_t* __restrict__ glist, int* __restrict__ cnt) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int H = a.H, W = a.W, HW = H * W;
+  __shared__ int swcount[kThreads / 32], swbase[kThreads / 32 + 1];
+  if (!sample_active(a, b)) { if (threadIdx.x == 0) cnt[(size_t)b * a.nchunks + chunk] = 0; return; }
+  const float fr = step_fire_rate(a);
+  const float* alpha = a.x_in + (size_t)b * C * HW + 3 * HW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kPerWarp = CH / (kThreads / 32);
+  const int cell0 = chunk * CH;
+  uint32_t bal[kPerWarp / 32];
+  int n = 0;
+#pragma unroll
+  for (int it = 0; it < kPerWarp / 32; ++it) {
+    const int cell = cell0 + warp * kPerWarp + it * 32 + lane;
+    bool act = false;
+    if (cell < HW) {
+      const int y = cell / W, x = cell - y * W;
+      act = alive_at(alpha, y, x, H, W, a.alpha_thr) && fires(a, fr, b, cell);
+    }
+    bal[it] = __ballot_sync(0xffffffffu, act);
+    n += __popc(bal[it]);
+  }
+  if (lane == 0) swcount[warp] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < kThreads / 32; ++w) { swbase[w] = s; s += swcount[w]; }
+    cnt[(size_t)b * a.nchunks + chunk] = s;
+  }
+  __syncthreads();
+  int base = swbase[warp];
+  uint16_t* dst = glist + (size_t)b * HW + cell0;            // chunk-local compact list (same order as k_update's own)
+#pragma unroll
+  for (int it = 0; it < kPerWarp / 32; ++it) {
+    if (bal[it] & (1u << lane)) dst[base + __popc(bal[it] & ((1u << lane) - 1u))] = (uint16_t)(warp * kPerWarp + it * 32 + lane);
+    base += __popc(bal[it]);
+  }
+}
+
+// exclusive prefix of the per-chunk counts of every sample: prefix[b][0..nchunks], one warp per sample
+__global__ void k_scan(int nchunks, const int* __restrict__ cnt, int* __restrict__ prefix) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int carry = 0;
+  for (int i0 = 0; i0 < nchunks; i0 += 32) {
+    const int i = i0 + lane;
+    const int v = i < nchunks ? cnt[(size_t)b * nchunks + i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (i < nchunks) prefix[(size_t)b * (nchunks + 1) + i] = carry + inc - v;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) prefix[(size_t)b * (nchunks + 1) + nchunks] = carry;
+}
+
+template <int C, int CH, bool BAL = false, int NT = kThreads, int JU = 4>
+__global__ void __launch_bounds__(NT) k_update(StepArgs a, Packed P, int hid, const float* __restrict__ packed,
+                                               const uint16_t* __restrict__ glist = nullptr,
+                                               const int* __restrict__ prefix = nullptr) {
+  static_assert(BAL || NT == kThreads, "the in-kernel compaction is written for kThreads threads");
   constexpr int PC = CellsPerThread<C>::value;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int H = a.H, W = a.W, HW = H * W;
   if (!sample_active(a, b)) return;
+  __shared__ int s_pf[BAL ? kMaxBalChunks + 1 : 1];
+  int r_lo = 0, r_hi = 0;
+  if constexpr (BAL) {
+    const int* pf = prefix + (size_t)b * (a.nchunks + 1);
+    const int total = pf[a.nchunks];
+    constexpr int RANGE = (CH + NT - 1) / NT * NT;      // active cells per block: whole rounds of NT (>= CH: nchunks blocks cover them)
+    r_lo = chunk * RANGE;
+    r_hi = min(r_lo + RANGE, total);
+    if (r_lo >= total) {                       // no work: this block's GroupNorm partial is zero
+      if (threadIdx.x == 0) {
+        a.partials[((size_t)b * a.nchunks + chunk) * 2] = 0.0;
+        a.partials[((size_t)b * a.nchunks + chunk) * 2 + 1] = 0.0;
+      }
+      return;
+    }
+    for (int i = threadIdx.x; i <= a.nchunks; i += NT) s_pf[i] = pf[i];
+  }
   const bool graph = (a.flags & GNCA_F_GRAPH) != 0;
   const float gain_m = graph ? step_message_gain(a) : 0.f;
   const float fr = step_fire_rate(a);
@@ -203,6 +287,8 @@ __global__ void __launch_bounds__(kThreads) k_update(StepArgs a, Packed P, int h
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kPerWarp = CH / (kThreads / 32);      // cells per warp
   const int cell0 = chunk * CH;
+  int nact = 0;
+  if constexpr (!BAL) {
   uint32_t bal[kPerWarp / 32];
   int cnt = 0;
 #pragma unroll
@@ -234,18 +320,33 @@ __global__ void __launch_bounds__(kThreads) k_update(StepArgs a, Packed P, int h
     }
   }
   __syncthreads();
-  const int nact = swbase[kThreads / 32];
+  nact = swbase[kThreads / 32];
+  } else {
+    __syncthreads();                            // weights and the prefix table are in shared memory
+    nact = r_hi - r_lo;
+  }
+  // rank -> cell through the per-chunk prefix (BAL) or this block's own list
+  auto cell_of = [&](int li) -> int {
+    if constexpr (BAL) {
+      const int rank = r_lo + li;
+      int lo = 0, hi = a.nchunks;                // s_pf[lo] <= rank < s_pf[hi]
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pf[mid] <= rank) lo = mid; else hi = mid; }
+      return lo * CH + (int)glist[(size_t)b * HW + (size_t)lo * CH + (rank - s_pf[lo])];
+    } else {
+      return cell0 + (int)slist[li];
+    }
+  };
 
   // ---- perception + MLP + message on active cells ------------------------------------------------
   float s1 = 0.f, s2 = 0.f;
-  for (int base = 0; base < nact; base += kThreads * PC) {
+  for (int base = 0; base < nact; base += NT * PC) {
     float yv[PC][3 * C];
     float dxv[PC][C];
     int cells[PC];
 #pragma unroll
     for (int p = 0; p < PC; ++p) {
-      const int li = base + p * kThreads + threadIdx.x;
-      cells[p] = li < nact ? cell0 + (int)slist[li] : -1;
+      const int li = base + p * NT + threadIdx.x;
+      cells[p] = li < nact ? cell_of(li) : -1;
       if (cells[p] >= 0) {
         const int y = cells[p] / W, x = cells[p] - y * W;
         perceive<C>(xs_base, y, x, H, W, yv[p]);
@@ -254,7 +355,7 @@ __global__ void __launch_bounds__(kThreads) k_update(StepArgs a, Packed P, int h
         for (int k = 0; k < 3 * C; ++k) yv[p][k] = 0.f;
       }
     }
-    mlp_forward<C, PC>(yv, dxv, sW1T, sb1, sW2T, hid);
+    mlp_forward<C, PC, JU>(yv, dxv, sW1T, sb1, sW2T, hid);
 #pragma unroll
     for (int p = 0; p < PC; ++p) {
       if (cells[p] < 0) continue;
@@ -284,10 +385,23 @@ __global__ void __launch_bounds__(kThreads) k_update(StepArgs a, Packed P, int h
   __syncthreads();
   if (threadIdx.x == 0) {
     double t1 = 0.0, t2 = 0.0;
-    for (int w = 0; w < kThreads / 32; ++w) { t1 += sred[w * 2]; t2 += sred[w * 2 + 1]; }
+    for (int w = 0; w < NT / 32; ++w) { t1 += sred[w * 2]; t2 += sred[w * 2 + 1]; }
     a.partials[((size_t)b * a.nchunks + chunk) * 2] = t1;
     a.partials[((size_t)b * a.nchunks + chunk) * 2 + 1] = t2;
   }
+}
+
+// (sum u, sum u^2) of sample b from the chunk partials, by ONE WARP: lane l adds chunks l, l+32, ... in order, then a
+// fixed shuffle tree -- the same arithmetic wherever the statistics are finished (k_apply, k_finalize_stats), and one
+// L2 round trip instead of nchunks dependent ones (k_apply starts every tile with this reduction).
+__device__ __forceinline__ void warp_reduce_partials(const StepArgs& a, int b, int lane, double& t1, double& t2) {
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = lane; i < a.nchunks; i += 32) {
+    s1 += a.partials[((size_t)b * a.nchunks + i) * 2];
+    s2 += a.partials[((size_t)b * a.nchunks + i) * 2 + 1];
+  }
+  t1 = warp_sum(s1);
+  t2 = warp_sum(s2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -320,14 +434,11 @@ __global__ void __launch_bounds__(kThreads) k_apply(StepArgs a, Packed P, const 
   const float fr = step_fire_rate(a);
   const bool gn = (a.flags & GNCA_F_GROUPNORM) != 0;
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
     float mu = 0.f, rstd = 1.f;
     if (gn) {
-      double t1 = 0.0, t2 = 0.0;
-      for (int i = 0; i < a.nchunks; ++i) {
-        t1 += a.partials[((size_t)b * a.nchunks + i) * 2];
-        t2 += a.partials[((size_t)b * a.nchunks + i) * 2 + 1];
-      }
+      double t1, t2;
+      warp_reduce_partials(a, b, threadIdx.x, t1, t2);
       const double n = (double)C * (double)HW;
       const double m = t1 / n;
       double var = t2 / n - m * m;
@@ -335,8 +446,10 @@ __global__ void __launch_bounds__(kThreads) k_apply(StepArgs a, Packed P, const 
       mu = (float)m;
       rstd = (float)(1.0 / sqrt(var + (double)a.gn_eps));
     }
-    s_stat[0] = mu; s_stat[1] = rstd;
-    if (blockIdx.x == 0 && a.stats) { a.stats[b * 2] = mu; a.stats[b * 2 + 1] = rstd; }
+    if (threadIdx.x == 0) {
+      s_stat[0] = mu; s_stat[1] = rstd;
+      if (blockIdx.x == 0 && a.stats) { a.stats[b * 2] = mu; a.stats[b * 2 + 1] = rstd; }
+    }
   }
   __syncthreads();
   if (threadIdx.x < C) {
@@ -484,6 +597,49 @@ void fill_step_args(StepArgs& a, const gnca_model& m, int B, int H, int W) {
   a.nchunks = (H * W + a.chunk - 1) / a.chunk;
 }
 
+// k_update launch: per-chunk compaction inside the kernel (small problems) or the balanced global list (large ones).
+// The global list lives in ws.absmean (one uint16 per cell; the attention-map kernels that own that buffer run after
+// k_apply), the per-chunk counts and their prefix in the part of ws.partials that only small-chunk runs use.
+template <int C>
+static int launch_update(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const FwdWorkspace& ws,
+                         cudaStream_t st) {
+  const bool graph = (m.flags & GNCA_F_GRAPH) != 0;
+  const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
+  dim3 g1(a.nchunks, a.B);
+  if (a.chunk == kChunkSmall) {
+    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_update<C, kChunkSmall><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
+    return 0;
+  }
+  const int HW = a.H * a.W;
+  const int n_small = (HW + kChunkSmall - 1) / kChunkSmall;
+  const size_t used = (size_t)a.B * a.nchunks * 2 * sizeof(double), have = (size_t)a.B * n_small * 2 * sizeof(double);
+  const size_t need = ((size_t)a.B * a.nchunks + (size_t)a.B * (a.nchunks + 1)) * sizeof(int);
+  static const bool no_bal = getenv("GNCA_NO_BALANCE") != nullptr;            // development: the per-chunk kernel
+  if (!no_bal && a.nchunks <= kMaxBalChunks && used + need <= have) {
+    int* cnt = reinterpret_cast<int*>(reinterpret_cast<char*>(ws.partials) + used);
+    int* prefix = cnt + (size_t)a.B * a.nchunks;
+    uint16_t* glist = reinterpret_cast<uint16_t*>(ws.absmean);
+    k_compact<kChunk><<<g1, kThreads, 0, st>>>(a, C, glist, cnt);
+    k_scan<<<a.B, 32, 0, st>>>(a.nchunks, cnt, prefix);
+    if constexpr (C >= 16) {
+      // 384 threads (168 registers, no spills): 12 warps per SM instead of 8 hide the perception / sender loads better
+      // (measured at 256x256x32: 9.99 -> 9.31 ms per 20 steps; 8 hidden units per pass and 256 threads were slower)
+      GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk, true, kThreadsBal>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_update<C, kChunk, true, kThreadsBal><<<g1, kThreadsBal, smem, st>>>(a, P, m.hidden, packed, glist, prefix);
+      g_launches += 2;
+      return 0;
+    }
+    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_update<C, kChunk, true><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed, glist, prefix);
+    g_launches += 2;
+    return 0;
+  }
+  GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_update<C, kChunk><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
+  return 0;
+}
+
 template <int C>
 int launch_step_fwd(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const FwdWorkspace& ws,
                     float* attn_out, cudaStream_t st) {
@@ -495,16 +651,8 @@ int launch_step_fwd(const gnca_model& m, const Packed& P, const float* packed, S
     int rc = run_attn_prepass(m, P, packed, a, ws, st);
     if (rc) return rc;
   }
-  const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
-  dim3 g1(a.nchunks, a.B);
   prof_begin(PROF_UPDATE, st);
-  if (a.chunk == kChunkSmall) {
-    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_update<C, kChunkSmall><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
-  } else {
-    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_update<C, kChunk><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
-  }
+  { const int rc = launch_update<C>(m, P, packed, a, ws, st); if (rc) return rc; }
   prof_end(PROF_UPDATE, st);
   GNCA_LAUNCH_CHECK();
   const int tiles = ((a.W + kTileW - 1) / kTileW) * ((a.H + kTileH - 1) / kTileH);
@@ -558,16 +706,13 @@ int dispatch_step_fwd(const gnca_model& m, const Packed& P, const float* packed,
 }
 
 // (mean, rstd) from the chunk partials -- used when only u is recomputed (backward of a rollout)
-__global__ void k_finalize_stats(StepArgs a, int C) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_finalize_stats(StepArgs a, int C) {       // one warp per sample
+  const int b = blockIdx.x, lane = threadIdx.x;
   if (b >= a.B || !a.stats) return;
   float mu = 0.f, rstd = 1.f;
   if (a.flags & GNCA_F_GROUPNORM) {
-    double t1 = 0.0, t2 = 0.0;
-    for (int i = 0; i < a.nchunks; ++i) {
-      t1 += a.partials[((size_t)b * a.nchunks + i) * 2];
-      t2 += a.partials[((size_t)b * a.nchunks + i) * 2 + 1];
-    }
+    double t1, t2;
+    warp_reduce_partials(a, b, lane, t1, t2);
     const double n = (double)C * (double)a.H * (double)a.W;
     const double m = t1 / n;
     double var = t2 / n - m * m;
@@ -575,6 +720,7 @@ __global__ void k_finalize_stats(StepArgs a, int C) {
     mu = (float)m;
     rstd = (float)(1.0 / sqrt(var + (double)a.gn_eps));
   }
+  if (lane != 0) return;
   a.stats[b * 2] = mu; a.stats[b * 2 + 1] = rstd;
 }
 
@@ -588,17 +734,9 @@ int launch_step_recompute(const gnca_model& m, const Packed& P, const float* pac
     int rc = run_attn_prepass(m, P, packed, a, ws, st);
     if (rc) return rc;
   }
-  const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
-  dim3 g1(a.nchunks, a.B);
-  if (a.chunk == kChunkSmall) {
-    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_update<C, kChunkSmall><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
-  } else {
-    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_update<C, kChunk><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
-  }
+  { const int rc = launch_update<C>(m, P, packed, a, ws, st); if (rc) return rc; }
   GNCA_LAUNCH_CHECK();
-  k_finalize_stats<<<(a.B + 127) / 128, 128, 0, st>>>(a, C);
+  k_finalize_stats<<<a.B, 32, 0, st>>>(a, C);
   GNCA_LAUNCH_CHECK();
   return 0;
 }
