@@ -493,16 +493,29 @@ __global__ void __launch_bounds__(kThreads) k_apply(StepArgs a, Packed P, const 
     for (int j = 0; j < 3; ++j) mx = fmaxf(mx, s_alpha[ly + i][lx + j]);
   const bool post = mx > a.alpha_thr;
   const float* up = a.u + (size_t)b * C * HW + cell;
+  // all loads of a group of channels are issued before the first use: the kernel is a pure HBM stream and a warp that
+  // keeps only a few loads in flight (the compiler's choice at 32 registers) leaves it latency-bound
+  constexpr int CG = C < 16 ? C : 16;
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    float v;
-    if (c == 3) {
-      v = post ? s_alpha[ly + 1][lx + 1] : 0.f;     // x~_3 * post_alive (ncagraph.py:158-166)
-    } else {
-      const float xin = xs_base[c * HW + cell];
-      v = xin + (act ? tanhf(fmaf(up[(size_t)c * HW], s_sc[c], s_bi[c])) * a.update_gain : s_idle[c]);
+  for (int c0 = 0; c0 < C; c0 += CG) {
+    float xin[CG], uu[CG];
+#pragma unroll
+    for (int j = 0; j < CG; ++j) {
+      const int c = c0 + j;
+      xin[j] = (c == 3) ? 0.f : __ldg(xs_base + (size_t)c * HW + cell);
+      uu[j] = (act && c != 3) ? __ldg(up + (size_t)c * HW) : 0.f;
     }
-    xo_base[c * HW + cell] = v;
+#pragma unroll
+    for (int j = 0; j < CG; ++j) {
+      const int c = c0 + j;
+      float v;
+      if (c == 3) {
+        v = post ? s_alpha[ly + 1][lx + 1] : 0.f;     // x~_3 * post_alive (ncagraph.py:158-166)
+      } else {
+        v = xin[j] + (act ? tanhf(fmaf(uu[j], s_sc[c], s_bi[c])) * a.update_gain : s_idle[c]);
+      }
+      xo_base[(size_t)c * HW + cell] = v;
+    }
   }
 }
 
