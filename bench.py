@@ -41,7 +41,11 @@ FLOP_FWDBWD_GRAPH_S = 53.6e3
 FLOP_FWD_GRAPH_L = 36.7e3
 FP32_LANES = 148 * 128 * 2           # FMA lanes x 2 flop
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_DRAM_BYTES = {("c2", "k_rep_fwd"): 1090304}     # profiles/r01_rep_fwd_summary.md: 1.090304 MB read, 0 written (x_T still in L2)
+NCU_DRAM_BYTES = {("c2", "k_rep_fwd"): 1090304,     # profiles/r01_rep_fwd_summary.md: 1.090304 MB read, 0 written (x_T still in L2)
+                  ("c5", "k_update"): 112492544}    # profiles/r01_k_update_summary.md (B=16 slice): 81.27 MB read + 31.22 MB written
+# sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active of the same captures: the REAL pipe utilisation next to the
+# dense-equivalent fraction (which counts the flops of the cells the kernels skip)
+NCU_FMA_PIPE_PCT = {("c2", "k_rep_fwd"): 18.1, ("c3", "k_rep_bwd"): 26.3, ("c5", "k_update"): 31.8}
 
 
 def load_weights(name):
@@ -375,7 +379,8 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
             peak = FP32_LANES * mhz * 1e6 / 1e12
             achieved = flops_per_launch / avg_s / 1e12
             roof = {"bound": "fp32_fma", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": NCU_DRAM_BYTES.get((cfg["name"][:2], kname)), "avg_launch_ms": avg_s * 1e3, "launches_per_step": n / nprof,
+                    "frac": achieved / peak, "traffic": NCU_DRAM_BYTES.get((cfg["name"][:2], kname)) if (cfg["name"][:2] != "c5" or B == 16) else None,
+                    "fma_pipe_pct_ncu": NCU_FMA_PIPE_PCT.get((cfg["name"][:2], kname)), "avg_launch_ms": avg_s * 1e3, "launches_per_step": n / nprof,
                     "peak_source": f"derived: 148 SM x 128 FMA lanes x 2 x {mhz} MHz (MEASURED_PEAKS.json has no fp32 entry; "
                                    "hbm_gbs 6547.8 measured is far from binding: see hbm_view)",
                     "note": "achieved = DENSE algorithmic flops (every cell counted) / measured kernel time; the kernel "
