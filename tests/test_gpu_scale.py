@@ -1,0 +1,97 @@
+"""BASELINE configs[4] shape (256x256 grid, 32 channels, hidden 128, torus graph path) on the GPU: one step against the
+CPU oracle, and the size-independent properties of the rollout at that shape (the oracle does not finish a 1000-step
+rollout of this size in test time): bitwise run-to-run determinism, frozen samples pass through, samples are
+independent (a permuted batch gives the permuted result bit for bit), damage at step t == multiply + continue.
+All of it runs the streaming kernels in their large-problem (balanced k_update) mode."""
+import random
+
+import pytest
+import torch
+
+from conftest import max_rel, rel_err
+from oracle import nca_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import graph_neural_cellular_automata_b200 as G
+    from graph_neural_cellular_automata_b200 import functional as GF
+    from graph_neural_cellular_automata_b200.rollout import make_schedule, rollout
+    from graph_neural_cellular_automata_b200.utils.damage import circle_mask
+
+DEV = "cuda"
+C, H, W, HID = 32, 256, 256, 128
+
+
+def _model():
+    torch.manual_seed(5); random.seed(5)
+    m = G.NeuralCAGraph(C, update_hidden=HID, img_size=H, update_gain=0.1, alpha_thr=0.1, message_gain=0.3,
+                        hidden_only=True, graph_zero_padded_shift=False)
+    with torch.no_grad():
+        m.update_net[2].weight.normal_(0, 0.05)
+        m.norm.weight.uniform_(0.5, 1.5); m.norm.bias.normal_(0, 0.1)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    return m.to(DEV), p
+
+
+def _blobs(B):
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    disk = (((yy - H / 2) ** 2 + (xx - W / 2) ** 2) < (0.3 * H) ** 2).float()
+    x = torch.rand(B, C, H, W) * disk
+    x[1::2, 3] *= (torch.rand((B + 0) // 2, H, W) > 0.4).float()        # ragged alive sets on every other sample
+    return x
+
+
+def test_one_step_vs_oracle_at_scale():
+    m, p = _model()
+    B = 5                                            # 5 * 64 chunks >= 2 * 148 blocks: the balanced large-problem path
+    x = _blobs(B)
+    fu = torch.rand(B, 1, H, W)
+    chosen = random.sample(m.graph.offsets, 8)
+    cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=True, message_gain=0.3, hidden_only=True,
+                       zero_padded_shift=False)
+    ref = O.nca_step(x, p, cfg, 0.5, fu, chosen)
+    with torch.no_grad():
+        out = m.step(x.to(DEV), 0.5, fire_u=fu.to(DEV), chosen=chosen)
+    assert max_rel(out.cpu(), ref) < 1e-5, max_rel(out.cpu(), ref)           # 1e-5 relative, single step (north star)
+    assert rel_err(out.cpu(), ref) < 1e-5
+    assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref, 0.1))  # alive mask bit-exact
+
+
+def test_rollout_properties_at_scale():
+    m, _ = _model()
+    B, T, td = 6, 5, 2
+    x0 = _blobs(B).to(DEV)
+    random.seed(11)
+    offs = [m.graph.draw_offsets() for _ in range(T)]
+    fu = torch.rand(T, B, H, W, device=DEV)
+    D = circle_mask(x0, 40).expand_as(x0).contiguous()
+    steps = [T, T, 0, 3, T, 1]                        # sample 2 is frozen from the start, 3 and 5 stop early
+
+    def run(x, f, d, st):
+        sched = make_schedule(m, x.shape[0], H, W, T, fire_rate=0.5, offsets=offs, fire_u=f, damage=d, damage_step=td,
+                              steps=st)
+        with torch.no_grad():
+            return rollout(m, x, sched)
+
+    a = run(x0, fu, D, steps)
+    # (1) bitwise deterministic run to run
+    assert torch.equal(a, run(x0, fu, D, steps))
+    # (2) frozen sample: untouched by the steps (train...:306-321 `state[mask] = model(state[mask])`); the damage of the
+    #     batch is still applied to it at t = td, as the reference's in-place damage on the whole batch would
+    assert torch.equal(a[2], x0[2] * D[2])
+    # (3) samples are independent: a permuted batch (inputs, masks, damage, step counts) gives the permuted result
+    perm = torch.tensor([3, 0, 5, 1, 4, 2], device=DEV)
+    b = run(x0[perm].contiguous(), fu[:, perm].contiguous(), D[perm].contiguous(), [steps[i] for i in perm.tolist()])
+    assert torch.equal(b, a[perm])
+    # (4) damage at step td == rollout to td, multiply, continue (regeneration protocol)
+    full = [T] * B
+    whole = run(x0, fu, D, full)
+    sched1 = make_schedule(m, B, H, W, td, fire_rate=0.5, offsets=offs[:td], fire_u=fu[:td].contiguous())
+    sched2 = make_schedule(m, B, H, W, T - td, fire_rate=0.5, offsets=offs[td:], fire_u=fu[td:].contiguous())
+    with torch.no_grad():
+        mid = rollout(m, x0, sched1)
+        two = rollout(m, (mid * D).contiguous(), sched2)
+    assert torch.equal(whole, two)
+    # (5) the state stays finite and alive
+    assert torch.isfinite(whole).all() and float((whole[:, 3] > 0.1).float().mean()) > 0.01
