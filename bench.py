@@ -116,7 +116,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)       # the default timed region is ~20 ms: sample densely enough to see it
 
     def result(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,

@@ -287,6 +287,8 @@ def rollout(model, x0: torch.Tensor, schedule: Schedule, *, return_history: bool
         raise RuntimeError(f"rollout: x0 is on {x0.device}; CUDA (sm_100a) only, no CPU fallback")
     ps = model.canonical_params()
     need_grad = torch.is_grad_enabled() and (x0.requires_grad or any(p.requires_grad for p in ps))
+    if not need_grad and not return_history:        # inference: no autograd node, no history (same C call underneath)
+        return rollout_fwd_raw(model.model_desc(), model.packed_weights(), x0, schedule, history=False, impl=IMPL[impl])[0]
     cfg = {"desc": model.model_desc(), "packed": model.packed_weights(), "schedule": schedule, "need_grad": need_grad,
            "history": bool(return_history), "impl": IMPL[impl]}
     return _RolloutFn.apply(x0, cfg, *ps)
