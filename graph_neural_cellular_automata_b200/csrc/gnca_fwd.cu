@@ -640,11 +640,10 @@ static int launch_update(const gnca_model& m, const Packed& P, const float* pack
       // (measured at 256x256x32: 9.99 -> 9.31 ms per 20 steps; 8 hidden units per pass and 256 threads were slower)
       GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk, true, kThreadsBal>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_update<C, kChunk, true, kThreadsBal><<<g1, kThreadsBal, smem, st>>>(a, P, m.hidden, packed, glist, prefix);
-      g_launches += 2;
-      return 0;
+    } else {
+      GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_update<C, kChunk, true><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed, glist, prefix);
     }
-    GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_update<C, kChunk, true><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed, glist, prefix);
     g_launches += 2;
     return 0;
   }

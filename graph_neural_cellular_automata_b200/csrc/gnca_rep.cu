@@ -375,9 +375,6 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
   __syncthreads();
   prepare_from_state(0);
 
-  // peers: 32-bit shared::cluster address deltas (the distributed shared window is linear per rank)
-  {
-  }
   const uint32_t mbarA = smem_u32(&s_mbar[0]), mbarB = smem_u32(&s_mbar[1]);
   const bool use_async = R.use_async != 0 && NC > 1;
   if (tid == 0) {

@@ -36,7 +36,6 @@ namespace gnca {
 constexpr int kQT = 512;          // threads per CTA (k_rep_bwd)
 constexpr int kQW = kQT / 32;
 constexpr int kQW2S = 20;         // padded row stride of W2^T
-constexpr int kQG = 4;            // cells per tile
 constexpr int kQW1S = 132;        // padded row stride of W1^T (floats): rows c, c+8 share banks only pairwise (2-way)
 
 struct RepBwdArgs {
@@ -116,7 +115,6 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   __shared__ float s_wred[kQW][2];
   __shared__ float s_chs[kQW][2][C];       // per-warp per-channel sums (A0)
   __shared__ float s_aff[4][C];            // sc, bi, k_c = eta(1 - tanh(bi)^2), inactive gz factor ...
-  __shared__ float s_sums[2];
   __shared__ signed char s_off[2 * 16];
   __shared__ float s_gain;
   __shared__ int s_bandbase[2];            // slot of the first active cell at / after band_lo, band_hi
@@ -136,7 +134,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   __shared__ __align__(16) float s_wmT[C][C + 4];               // s_wmT[c][cc] = Wm[cc][c] (kept out of the registers)
 #pragma unroll
   for (int cc = 0; cc < C; ++cc) if (tid < C) s_wmT[tid][cc] = graph ? packed[P.wm + cc * C + tid] : 0.f;
-  const float gam_c = gn ? packed[P.gamma + c] : 1.f, bet_c = gn ? packed[P.beta + c] : 0.f;
+  const float gam_c = gn ? packed[P.gamma + c] : 1.f;
 
   const size_t sample_off = (size_t)b * C * HW;
   float* GZs = R.GZ + (size_t)b * HW * C;
@@ -162,7 +160,6 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   const int my_steps = a.steps ? min(a.steps[b], R.T) : R.T;
   const int q = tid, qcell = 4 * tid;
   const bool qv = q < NQ;
-  const int qy = qcell / W, qx0 = qcell - qy * W;
   const int qsh = 4 * (lane & 7), qword = min(q >> 3, kMaskWords - 1);
   float* myY = sY + warp * (C3 * GM);
   float* myGD = sGD + warp * (C * GM);
@@ -249,6 +246,16 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       }
     }
     const int bandbase = s_bandbase[0], n_band = s_bandbase[1] - s_bandbase[0];
+    // u of my band's active cells (phase A) is requested NOW: one L2 round trip that phase A0 overlaps, instead of
+    // n_band / 32 dependent ones at the top of phase A (the record loads were 5 % of the kernel's stall samples)
+    constexpr int kAPre = 6;                 // 6 x 32 band cells up front; a longer band list falls back to the loop
+    const size_t rec_base = ((size_t)t * a.B + b) * HW;
+    float upre[kAPre];
+#pragma unroll
+    for (int i = 0; i < kAPre; ++i) {
+      const int bi_ = warp * CPL + hwi + i * (kQW * CPL);
+      upre[i] = bi_ < n_band ? __ldcg(R.rec + (rec_base + bandbase + bi_) * kRecStride + kRecU + c) : 0.f;
+    }
     REPB_MARK(1);
     // ---- A0: inactive cells of my band: per-channel sums of the gated gradient --------------------------------------
     float s1 = 0.f, s2 = 0.f;
@@ -280,13 +287,10 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
     // ---- A: active cells of my BAND (g is resident here): gz = gated g * eta * (1 - tanh^2(gn(u)))  -> GZ[slot] in L2
     //         (ncagraph.py:153-166 backward); the heavy part (B) is done by whichever CTA the balanced split picks
     const float sc_c = s_aff[0][c], bi_c = s_aff[1][c];
-    const size_t rec_base = ((size_t)t * a.B + b) * HW;
-#pragma unroll 2
-    for (int bi_ = warp * CPL + hwi; bi_ < n_band; bi_ += kQW * CPL) {
+    auto band_cell = [&](const int bi_, const float u) {
       const int cell = s_blist[bi_];
       float g = sG[(cell - band_lo) * C + c];
       if (c == 3 && !((s_bPost[cell >> 5] >> (cell & 31)) & 1u)) g = 0.f;
-      const float u = __ldcg(R.rec + (rec_base + bandbase + bi_) * kRecStride + kRecU + c);
       const float th = tanhf(fmaf(u, sc_c, bi_c));
       const float gz = g * eta * (1.f - th * th);
       GZs[(size_t)(bandbase + bi_) * C + c] = gz;
@@ -295,7 +299,15 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
         s1 += gu; s2 = fmaf(gu, uh, s2);
         dgam = fmaf(gz, uh, dgam); dbet += gz;
       }
+    };
+#pragma unroll
+    for (int i = 0; i < kAPre; ++i) {
+      const int bi_ = warp * CPL + hwi + i * (kQW * CPL);
+      if (bi_ < n_band) band_cell(bi_, upre[i]);
     }
+#pragma unroll 2
+    for (int bi_ = warp * CPL + hwi + kAPre * (kQW * CPL); bi_ < n_band; bi_ += kQW * CPL)
+      band_cell(bi_, __ldcg(R.rec + (rec_base + bandbase + bi_) * kRecStride + kRecU + c));
     REPB_MARK(3);
     // ---- S1, S2: warp -> block -> every CTA of the cluster ---------------------------------------------------------
     {

@@ -116,7 +116,6 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
   const int nown = own * W;                  // own cells
   const int PL = R.plane_stride;             // padded plane stride (== 1 mod 32: bank-conflict free across channels)
   const int MB = R.MB, MBP = MB + 4;
-  const int JG = hid >> 7;                   // groups of 128 hidden units (hid % 128 == 0)
   const int kk = a.k > 0 ? a.k : 1;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,7 +143,7 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
   signed char* s_off = reinterpret_cast<signed char*>(s_gain + R.T);        // [T][k][2] offsets
   __shared__ float s_partsf[8][2];           // (sum u, sum u^2) of every CTA of the cluster, pushed by its owner
   __shared__ float s_wredf[kRWarps][2];
-  __shared__ float s_sc[C], s_bi[C], s_idle[C], s_gam[C], s_bet[C], s_stat[2];
+  __shared__ float s_sc[C], s_bi[C], s_idle[C], s_gam[C], s_bet[C];
   __shared__ int s_wcount[kRWarps], s_wbase[kRWarps + 1];
   __shared__ unsigned long long s_dbg[16];
   if (tid < 16) s_dbg[tid] = 0;
