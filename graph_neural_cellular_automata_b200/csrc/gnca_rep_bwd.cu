@@ -70,6 +70,19 @@ struct RepBwdArgs {
 #define REPB_MARK(idx) do { } while (0)
 #endif
 
+// Bulk asynchronous stores shared -> global (async proxy, tracked per thread in bulk groups).  The 1 KB per record of
+// h | gh that only k_rep_wgrad reads goes out this way: the cluster barriers' release fence then no longer waits for
+// those stores to drain (they were ~70 % of the bytes a CTA writes per step), and the warp issues 2 instructions per
+// cell instead of 16 STG.128.
+__device__ __forceinline__ void bulk_store_512(float* gdst, const float* ssrc) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 512;" ::"l"(__cvta_generic_to_global(gdst)),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void cl_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
@@ -405,14 +418,23 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       }
       // gh[m][jj] = [h > 0] * sum_c W2[c][j] gd[c][m]   (the ReLU mask as bits, the accumulators reuse acc1's registers)
       uint32_t hmask = 0;
+      // h rows -> the warp's smem tile -> one 512-byte bulk store per cell (lane m issues cell m); the tile's previous
+      // bulk reads (gh of the warp's last tile) must have finished before it is overwritten
+      float* const hgh_row = R.hgh + (rec_base + lo_my + slot0 + min(lane, G - 1)) * kHghStride;
+      const bool issuer = lane < G && slot0 + lane < lim;
+      if (lane < G) bulk_wait_read_all();
+      __syncwarp();
 #pragma unroll
       for (int m = 0; m < G; ++m) {
-        if (slot0 + m < lim)
-          *reinterpret_cast<float4*>(R.hgh + (rec_base + lo_my + slot0 + m) * kHghStride + 4 * lane) =
-              make_float4(fmaxf(acc1[m][0], 0.f), fmaxf(acc1[m][1], 0.f), fmaxf(acc1[m][2], 0.f), fmaxf(acc1[m][3], 0.f));
+        *reinterpret_cast<float4*>(myGH + m * HID + 4 * lane) =
+            make_float4(fmaxf(acc1[m][0], 0.f), fmaxf(acc1[m][1], 0.f), fmaxf(acc1[m][2], 0.f), fmaxf(acc1[m][3], 0.f));
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) { hmask |= acc1[m][jj] > 0.f ? (1u << (4 * m + jj)) : 0u; acc1[m][jj] = 0.f; }
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (issuer) bulk_store_512(hgh_row, myGH + lane * HID);
+      if (lane < G) bulk_commit();
 #pragma unroll
       for (int c4 = 0; c4 < C / 4; ++c4) {
         float4 w2[4];
@@ -442,15 +464,19 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
       // gy[kk][m] = sum_j W1[j][kk] gh[j][m].  gh goes through the warp's shared-memory tile so that the lane that owns
       // (cell hwi+2e, channel c) can run the three 128-long dot products itself (rows c, 16+c, 32+c of W1^T = identity /
       // sobel_x / sobel_y parts): no cross-lane reduction.
+      if (lane < G) bulk_wait_read_all();        // the h rows have left the tile (issued before the gh loop above)
+      __syncwarp();
 #pragma unroll
       for (int m = 0; m < G; ++m) {
         float4 v;
         v.x = (hmask >> (4 * m)) & 1u ? acc1[m][0] : 0.f; v.y = (hmask >> (4 * m + 1)) & 1u ? acc1[m][1] : 0.f;
         v.z = (hmask >> (4 * m + 2)) & 1u ? acc1[m][2] : 0.f; v.w = (hmask >> (4 * m + 3)) & 1u ? acc1[m][3] : 0.f;
         *reinterpret_cast<float4*>(myGH + m * HID + 4 * lane) = v;
-        if (slot0 + m < lim) *reinterpret_cast<float4*>(R.hgh + (rec_base + lo_my + slot0 + m) * kHghStride + HID + 4 * lane) = v;
       }
+      fence_proxy_async_smem();
       __syncwarp();
+      if (issuer) bulk_store_512(hgh_row + HID, myGH + lane * HID);
+      if (lane < G) bulk_commit();
       {
         float gy[3][MPL];
 #pragma unroll
@@ -617,6 +643,7 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
     for (int w = 0; w < kQW; ++w) ac += s_chs[w][which][ch];
     R.affpart[(size_t)blockIdx.x * 2 * C + tid] = ac;
   }
+  if (lane < 8) bulk_wait_all();               // every h | gh row has reached global memory before the kernel ends
   cl_sync_all();
 }
 
