@@ -45,7 +45,7 @@ NCU_DRAM_BYTES = {("c2", "k_rep_fwd"): 1090304,     # profiles/r01_rep_fwd_summa
                   ("c5", "k_update"): 112492544}    # profiles/r01_k_update_summary.md (B=16 slice): 81.27 MB read + 31.22 MB written
 # sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active of the same captures: the REAL pipe utilisation next to the
 # dense-equivalent fraction (which counts the flops of the cells the kernels skip)
-NCU_FMA_PIPE_PCT = {("c2", "k_rep_fwd"): 18.1, ("c3", "k_rep_bwd"): 26.3, ("c5", "k_update"): 31.8}
+NCU_FMA_PIPE_PCT = {("c2", "k_rep_fwd"): 18.1, ("c3", "k_rep_bwd"): 30.1, ("c5", "k_update"): 31.8}
 
 
 def load_weights(name):
