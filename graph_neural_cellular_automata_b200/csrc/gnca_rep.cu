@@ -57,7 +57,6 @@ struct RepArgs {
   int damage_step;
   unsigned long long* dbg;
   int dbg_cta;
-  int dbg_repeat;             // development (GNCA_REPEAT): bit0 = run the S4+S1 block twice (idempotent; cost = time delta)
   int use_async;              // 1: st.async + mbarrier transaction counts between the CTAs, 0: two cluster barriers per step
 };
 
@@ -759,7 +758,6 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     {
       // inactive cells: x_c += idle_c (their masked pre-norm update is 0, ncagraph.py:149-155); float4 per (cell, quad)
       const float4 i4 = *reinterpret_cast<const float4*>(&s_aff[2][4 * (tid & 3)]);
-      const float idle3 = s_aff[2][3];
       // item = tid + 512 j  <->  cell (tid>>2) + 128 j, channel quad tid&3: the active bit sits at a per-thread constant
       // position of word (tid>>7) + 4 j, and every address is a constant offset from a per-thread base
       float4* X4 = reinterpret_cast<float4*>(sX) + tid;
@@ -780,19 +778,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
         X4[nfull * kPT] = v;
       }
       REP_MARK(11);
-#pragma unroll 1
-      for (int q = tid; q < NQ; q += kPT) {
-        const uint32_t nib = (s_bAct[q >> 3] >> (4 * (q & 7))) & 15u;
-        const float4 ag = reinterpret_cast<const float4*>(sAg)[q];
-        if (nib == 0) {
-          reinterpret_cast<float4*>(sAt)[q] = make_float4(ag.x + idle3, ag.y + idle3, ag.z + idle3, ag.w + idle3);
-        } else {     // an active cell's slot is written by its owner (possibly remotely, already): scalar stores only
-          if (!(nib & 1u)) sAt[4 * q] = ag.x + idle3;
-          if (!(nib & 2u)) sAt[4 * q + 1] = ag.y + idle3;
-          if (!(nib & 4u)) sAt[4 * q + 2] = ag.z + idle3;
-          if (!(nib & 8u)) sAt[4 * q + 3] = ag.w + idle3;
-        }
-      }
+      // (the alpha of the inactive cells, alpha + idle_3, is formed in S4 where the plane is read anyway)
     }
     REP_MARK(4);
     if (use_async) {
@@ -805,8 +791,17 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
 
     // ---- S4 + S1 of the next step: post-alive gate (ncagraph.py:158-166) from bitmaps; pre_alive(t+1) ==
     //      post_alive(t) when both thresholds agree (a cell above thr is never gated), so one dilation serves both ----
-    for (int rep_ = 0; rep_ < ((R.dbg_repeat & 1) ? 2 : 1); ++rep_) {
+    const uint32_t nib_now = r_actnib;        // active cells of my quad in THIS step (act_count below replaces it)
+    const float idle3 = s_aff[2][3];
+    {
+      // updated alpha before the gate: active cells were written into sAt by their owners (locally or pushed), every
+      // other cell moves by the idle update of the alpha channel
       float4 at = reinterpret_cast<const float4*>(sAt)[ql];
+      {
+        const float4 ag = reinterpret_cast<const float4*>(sAg)[ql];
+        at.x = (nib_now & 1u) ? at.x : ag.x + idle3; at.y = (nib_now & 2u) ? at.y : ag.y + idle3;
+        at.z = (nib_now & 4u) ? at.z : ag.z + idle3; at.w = (nib_now & 8u) ? at.w : ag.w + idle3;
+      }
       pack_store(s_bRaw, nib_gt(at, thr) & vmask);
       __syncthreads();
       const uint32_t post = dil(s_bRaw);
@@ -930,7 +925,6 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = pick; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (getenv("GNCA_REPEAT")) R.dbg_repeat = atoi(getenv("GNCA_REPEAT"));
   { const char* e = getenv("GNCA_REP_SYNC"); R.use_async = !(e && e[0] == 'b'); }     // development: "barrier"
   if (debug)
     fprintf(stderr, "[gnca] replicated fwd: B=%d NC=%d ucap=%d over=%d smem=%zu maxActiveClusters=%d\n", B, pick,
