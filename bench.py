@@ -41,11 +41,11 @@ FLOP_FWDBWD_GRAPH_S = 53.6e3
 FLOP_FWD_GRAPH_L = 36.7e3
 FP32_LANES = 148 * 128 * 2           # FMA lanes x 2 flop
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_DRAM_BYTES = {("c2", "k_rep_fwd"): 1090304,     # profiles/r01_rep_fwd_summary.md: 1.090304 MB read, 0 written (x_T still in L2)
+NCU_DRAM_BYTES = {("c2", "k_rep_fwd"): 1090816,     # profiles/r01_rep_fwd_summary.md: 1.090304 MB read, 0 written (x_T still in L2)
                   ("c5", "k_update"): 112492544}    # profiles/r01_k_update_summary.md (B=16 slice): 81.27 MB read + 31.22 MB written
 # sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active of the same captures: the REAL pipe utilisation next to the
 # dense-equivalent fraction (which counts the flops of the cells the kernels skip)
-NCU_FMA_PIPE_PCT = {("c2", "k_rep_fwd"): 18.1, ("c3", "k_rep_bwd"): 30.1, ("c5", "k_update"): 31.8}
+NCU_FMA_PIPE_PCT = {("c2", "k_rep_fwd"): 18.5, ("c3", "k_rep_bwd"): 30.1, ("c5", "k_update"): 31.8}
 
 
 def load_weights(name):

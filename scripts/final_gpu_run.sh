@@ -13,3 +13,5 @@ python bench.py --workload c5s --steps 5 --warmup 3 --no-cpu-baseline > $O/r01_b
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r01_launches_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_update --launch-skip 30 -c 1 -f -o $O/r01_k_update python bench.py --workload c5s --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_ku.log 2>&1
 ls -la $O/*.json | tail -8
+ncu --set full --clock-control none --import-source on -k regex:k_rep_fwd --launch-skip 3 -c 1 -f -o $O/r01_rep_fwd python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-train-extra > $O/ncu_repfwd.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_rep_bwd --launch-skip 3 -c 1 -f -o $O/r01_rep_bwd python bench.py --workload c3 --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_repbwd.log 2>&1
