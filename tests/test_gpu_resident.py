@@ -94,8 +94,8 @@ def test_every_cluster_size_fwd_bwd(nc):
     _compare(m, x0, _sched(m, 3, 40, 40, 6, seed=5))
 
 
-def test_barrier_sync_mode_matches():
-    os.environ["GNCA_REP_SYNC"] = "barrier"
+def test_barrier_sync_mode_matches(monkeypatch):
+    monkeypatch.setenv("GNCA_REP_SYNC", "barrier")       # this test only: every other test runs the default st.async exchange
     m = graph_model(True)
     x0 = _grown_state(m, 2, 40, 40, steps=20)
     _compare(m, x0, _sched(m, 2, 40, 40, 5, seed=6))

@@ -142,3 +142,35 @@ def test_native_offset_sampling_is_the_python_stream():
         arr = m.graph.draw_offsets_array(T)
         assert random.getstate() == after                       # the stream continues exactly where T forwards leave it
         assert [[tuple(int(v) for v in o) for o in st] for st in arr] == [[tuple(o) for o in st] for st in ref]
+
+
+def test_words_sampler_reports_short_blocks_and_keeps_the_stream():
+    """gnca_host_sample_offsets_words: a block of raw MT19937 outputs that is too short is refused (the python side
+    retries with a longer one), a sufficient block reproduces random.sample and reports the words it consumed."""
+    import ctypes as C
+    import random
+    import numpy as np
+    from graph_neural_cellular_automata_b200 import _lib
+    from graph_neural_cellular_automata_b200.modules.graph_augmentation import build_offsets
+    lib = _lib.load()
+    offsets = build_offsets(4)
+    n, k, T = len(offsets), 8, 50
+    table = np.ascontiguousarray(np.asarray(offsets, dtype=np.int8).reshape(n, 2))
+    out = np.empty((T, k, 2), np.int8)
+    used = C.c_int32(0)
+    random.seed(99)
+    state = random.getstate()
+    m = 4 * T * k
+    words = random.getrandbits(32 * m).to_bytes(4 * m, "little")
+    # T * k draws need at least T * k words: a shorter block must be refused, not read past its end
+    rc = lib.gnca_host_sample_offsets_words(words, T * k - 1, table.ctypes.data, n, k, T, out.ctypes.data, C.byref(used))
+    assert rc == _lib.GNCA_ERR_UNSUPPORTED
+    rc = lib.gnca_host_sample_offsets_words(words, m, table.ctypes.data, n, k, T, out.ctypes.data, C.byref(used))
+    assert rc == 0 and T * k <= used.value <= m
+    random.setstate(state)
+    ref = [random.sample(offsets, k) for _ in range(T)]
+    after = random.getstate()
+    assert out.tolist() == [[list(o) for o in st] for st in ref]
+    random.setstate(state)
+    random.getrandbits(32 * used.value)              # skipping exactly `used` outputs lands on the reference's state
+    assert random.getstate() == after
