@@ -7,6 +7,7 @@
 // The cluster-resident multi-step kernel lives in gnca_resident.cu.
 #include "gnca_common.cuh"
 #include "gnca_internal.h"
+#include <cstdio>
 #include <vector>
 #include <utility>
 
@@ -339,6 +340,12 @@ __global__ void __launch_bounds__(NT) k_update(StepArgs a, Packed P, int hid, co
 
   // ---- perception + MLP + message on active cells ------------------------------------------------
   float s1 = 0.f, s2 = 0.f;
+#ifdef GNCA_PHASE_COUNTERS          /* development: where a round's cycles go (one thread of one working block prints) */
+  long long ph_t = clock64(), ph[3] = {0, 0, 0};
+#define UPD_MARK(i) do { const long long n_ = clock64(); ph[i] += n_ - ph_t; ph_t = n_; } while (0)
+#else
+#define UPD_MARK(i) do { } while (0)
+#endif
   for (int base = 0; base < nact; base += NT * PC) {
     float yv[PC][3 * C];
     float dxv[PC][C];
@@ -355,7 +362,9 @@ __global__ void __launch_bounds__(NT) k_update(StepArgs a, Packed P, int hid, co
         for (int k = 0; k < 3 * C; ++k) yv[p][k] = 0.f;
       }
     }
+    UPD_MARK(0);
     mlp_forward<C, PC, JU>(yv, dxv, sW1T, sb1, sW2T, hid);
+    UPD_MARK(1);
 #pragma unroll
     for (int p = 0; p < PC; ++p) {
       if (cells[p] < 0) continue;
@@ -378,7 +387,14 @@ __global__ void __launch_bounds__(NT) k_update(StepArgs a, Packed P, int hid, co
         s2 = fmaf(v, v, s2);
       }
     }
+    UPD_MARK(2);
   }
+#ifdef GNCA_PHASE_COUNTERS
+  if (BAL && blockIdx.x == 2 && blockIdx.y == 0 && (threadIdx.x == 0 || threadIdx.x == NT - 1) && a.t == 2)
+    printf("[k_update phases, block (2,0) thread %d, %d active cells] lookup+perception %lld  mlp %lld  message+store %lld cycles\n",
+           (int)threadIdx.x, nact, ph[0], ph[1], ph[2]);
+#endif
+#undef UPD_MARK
   // ---- deterministic block reduction of (sum u, sum u^2) ------------------------------------------
   double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
   if (lane == 0) { sred[warp * 2] = d1; sred[warp * 2 + 1] = d2; }
