@@ -46,6 +46,8 @@ struct Packed {
   int wmt;    // [C][C]      transposed       (in, out)
   int bm;     // [C]
   int wq, bq, wk, bk, scaling;  // [d][C],[d],[d][C],[d],[1]
+  int w1c;    // [2][hid x 3C]  update_net.0.weight split into tf32 (hi, lo), canonical no-swizzle K-major UMMA layout
+  int w2c;    // [2][C x hid]   update_net.2.weight, same (gnca_tc.cuh); filled when C % 8 == 0 and hid % 8 == 0
   int total;
 };
 
@@ -73,6 +75,8 @@ __host__ __device__ inline Packed make_packed(int C, int hid, int d, bool graph)
   } else {
     p.wm = p.wmt = p.bm = p.wq = p.bq = p.wk = p.bk = p.scaling = -1;
   }
+  p.w1c = o; o += 2 * hid * 3 * C;
+  p.w2c = o; o += 2 * C * hid;
   p.total = o;
   return p;
 }
@@ -135,6 +139,7 @@ struct StepArgs {
   float* stats;                       // [B][2]  (mean, rstd)
   double* partials;                   // [B][nchunks][2]
   int nchunks, chunk;                 // k_update work split: cells per block and blocks per sample
+  int npart;                          // GroupNorm partial slots per sample in `partials` (nchunks, or 3*nchunks: k_update_tc)
   Offsets off;                        // host-supplied offsets (single step)
 };
 

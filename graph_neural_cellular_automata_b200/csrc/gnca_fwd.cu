@@ -7,6 +7,7 @@
 // The cluster-resident multi-step kernel lives in gnca_resident.cu.
 #include "gnca_common.cuh"
 #include "gnca_internal.h"
+#include "gnca_tc.cuh"
 #include <cstdio>
 #include <vector>
 #include <utility>
@@ -59,6 +60,20 @@ __global__ void k_pack(gnca_layout L, Packed P, int C, int hid, int d, const flo
     dst[P.w2t + j * C + c] = v;
   }
   for (int i = tid; i < C; i += nth) { dst[P.gamma + i] = src[L.gamma + i]; dst[P.beta + i] = src[L.beta + i]; }
+  if ((C & 7) == 0 && (hid & 7) == 0) {      // tf32 (hi, lo) split of both MLP weights in the UMMA operand layout
+    for (int i = tid; i < hid * C3; i += nth) {
+      const int j = i / C3, k = i % C3;
+      const float v = src[L.w1 + i], hi = __uint_as_float(tc::tf32_rna(v)), lo = __uint_as_float(tc::tf32_rna(v - hi));
+      dst[P.w1c + tc::canon_idx(j, k, C3)] = hi;
+      dst[P.w1c + hid * C3 + tc::canon_idx(j, k, C3)] = lo;
+    }
+    for (int i = tid; i < C * hid; i += nth) {
+      const int c = i / hid, j = i % hid;
+      const float v = src[L.w2 + i], hi = __uint_as_float(tc::tf32_rna(v)), lo = __uint_as_float(tc::tf32_rna(v - hi));
+      dst[P.w2c + tc::canon_idx(c, j, hid)] = hi;
+      dst[P.w2c + C * hid + tc::canon_idx(c, j, hid)] = lo;
+    }
+  }
   if (P.wm >= 0) {
     for (int i = tid; i < C * C; i += nth) {
       int co = i / C, ci = i % C;
@@ -412,9 +427,9 @@ __global__ void __launch_bounds__(NT) k_update(StepArgs a, Packed P, int hid, co
 // L2 round trip instead of nchunks dependent ones (k_apply starts every tile with this reduction).
 __device__ __forceinline__ void warp_reduce_partials(const StepArgs& a, int b, int lane, double& t1, double& t2) {
   double s1 = 0.0, s2 = 0.0;
-  for (int i = lane; i < a.nchunks; i += 32) {
-    s1 += a.partials[((size_t)b * a.nchunks + i) * 2];
-    s2 += a.partials[((size_t)b * a.nchunks + i) * 2 + 1];
+  for (int i = lane; i < a.npart; i += 32) {
+    s1 += a.partials[((size_t)b * a.npart + i) * 2];
+    s2 += a.partials[((size_t)b * a.npart + i) * 2 + 1];
   }
   t1 = warp_sum(s1);
   t2 = warp_sum(s2);
@@ -624,6 +639,7 @@ void fill_step_args(StepArgs& a, const gnca_model& m, int B, int H, int W) {
   // small chunks when 1024-cell chunks would leave SMs idle (launch-latency-bound small grids)
   a.chunk = ((long long)B * ((H * W + kChunk - 1) / kChunk) < 2 * 148) ? kChunkSmall : kChunk;
   a.nchunks = (H * W + a.chunk - 1) / a.chunk;
+  a.npart = a.nchunks;
 }
 
 // k_update launch: per-chunk compaction inside the kernel (small problems) or the balanced global list (large ones).
@@ -636,13 +652,18 @@ static int launch_update(const gnca_model& m, const Packed& P, const float* pack
   const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
   dim3 g1(a.nchunks, a.B);
   if (a.chunk == kChunkSmall) {
+    a.npart = a.nchunks;
     GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_update<C, kChunkSmall><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
     return 0;
   }
   const int HW = a.H * a.W;
   const int n_small = (HW + kChunkSmall - 1) / kChunkSmall;
-  const size_t used = (size_t)a.B * a.nchunks * 2 * sizeof(double), have = (size_t)a.B * n_small * 2 * sizeof(double);
+  static_assert(kChunk == kTcChunk, "k_update_tc reads the chunk-local lists of k_compact<kChunk>");
+  static const bool no_tc = getenv("GNCA_NO_TC") != nullptr;                  // development: the FFMA kernel
+  const bool use_tc = !no_tc && update_tc_supported(m, a);
+  a.npart = use_tc ? 3 * a.nchunks : a.nchunks;
+  const size_t used = (size_t)a.B * a.npart * 2 * sizeof(double), have = (size_t)a.B * n_small * 2 * sizeof(double);
   const size_t need = ((size_t)a.B * a.nchunks + (size_t)a.B * (a.nchunks + 1)) * sizeof(int);
   static const bool no_bal = getenv("GNCA_NO_BALANCE") != nullptr;            // development: the per-chunk kernel
   if (!no_bal && a.nchunks <= kMaxBalChunks && used + need <= have) {
@@ -651,6 +672,10 @@ static int launch_update(const gnca_model& m, const Packed& P, const float* pack
     uint16_t* glist = reinterpret_cast<uint16_t*>(ws.absmean);
     k_compact<kChunk><<<g1, kThreads, 0, st>>>(a, C, glist, cnt);
     k_scan<<<a.B, 32, 0, st>>>(a.nchunks, cnt, prefix);
+    if (use_tc) {
+      g_launches += 2;
+      return launch_update_tc(m, P, packed, a, glist, prefix, st);
+    }
     if constexpr (C >= 16) {
       // 384 threads (168 registers, no spills): 12 warps per SM instead of 8 hide the perception / sender loads better
       // (measured at 256x256x32: 9.99 -> 9.31 ms per 20 steps; 8 hidden units per pass and 256 threads were slower)
@@ -663,6 +688,7 @@ static int launch_update(const gnca_model& m, const Packed& P, const float* pack
     g_launches += 2;
     return 0;
   }
+  a.npart = a.nchunks;
   GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_update<C, kChunk><<<g1, kThreads, smem, st>>>(a, P, m.hidden, packed);
   return 0;

@@ -48,6 +48,13 @@ int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, cons
                  const float* gout, float* gx, float* gparams, const FwdWorkspace& fws, void* bwd_ws, bool zero_partials,
                  bool reduce_partials, cudaStream_t st);
 
+// tensor-core k_update (gnca_update_tc.cu): the balanced large-problem path for C in {16, 32}, hidden 128.
+// glist / prefix: the global active list of k_compact / k_scan.  Sets a.npart (3 partial slots per chunk).
+constexpr int kTcChunk = 1024;
+bool update_tc_supported(const gnca_model& m, const StepArgs& a);
+int launch_update_tc(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const uint16_t* glist,
+                     const int* prefix, cudaStream_t st);
+
 // cluster-resident forward rollout (gnca_resident.cu); GNCA_ERR_UNSUPPORTED when the configuration has no
 // resident kernel (zero-padded graph shift, sample too large for the cluster's shared memory)
 int run_resident_fwd(const gnca_model& m, const Packed& P, const float* packed, int B, int H, int W,

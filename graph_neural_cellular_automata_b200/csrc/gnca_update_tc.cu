@@ -1,0 +1,273 @@
+// k_update_tc: the per-cell update MLP of the streaming step on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// Same contract as the balanced k_update of gnca_fwd.cu (masked pre-norm update u of the ACTIVE cells + GroupNorm
+// partial sums; nca.py:75-87, ncagraph.py:128-150), for C in {16, 32} and hidden = 128.  What changes is where the
+// 2*(3C*128 + 128*C) flops per cell run:
+//   * a persistent CTA per SM, three warpgroups; a warpgroup owns a TILE of 128 active cells, thread t <-> cell t;
+//   * the thread computes its cell's perception vector y (3C values) and graph message in registers, splits y into
+//     tf32 (hi, lo) and writes both with tcgen05.st into TENSOR MEMORY lane t -- the activations never touch shared
+//     memory;
+//   * layer 1: D1[128 cells x 128] = y W1^T as 3 x (3C/8) tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8, A from
+//     TMEM, B = the (hi, lo) split of W1 resident in shared memory in the canonical K-major layout):
+//     hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM;
+//   * epilogue 1 (tcgen05.ld, the thread reads ITS cell's 128 hidden units): + b1, ReLU, split, back to TMEM;
+//   * layer 2: D2[128 x C] = h W2^T the same way (N = C, K = 128); epilogue 2 adds the message and stores u.
+// Accuracy of the split (scratch/umma_probe.cu on a B200): max |err| 1.7e-6 against fp64 for outputs of magnitude ~1
+// (fp32 FFMA chain: 2.3e-7) -- inside the 1e-5 single-step bar of the north star, tests/test_gpu_scale.py.
+// One set of TMEM columns per CTA: the three warpgroups take turns on the tensor-core chain (named-barrier token,
+// ~8 k cycles per tile) while the other two run their load-latency-bound perception / sender gathers.
+#include "gnca_common.cuh"
+#include "gnca_internal.h"
+#include "gnca_tc.cuh"
+
+namespace gnca {
+
+using namespace tc;
+
+constexpr int kTcWG = 3;                    // warpgroups per CTA
+constexpr int kTcThreads = kTcWG * 128;
+constexpr int kTcRange = 1152;              // active cells (ranks) per unit = 3 rounds of 384; >= kTcChunk
+constexpr int kTcHid = 128;
+constexpr int kBarTurn = 1;                 // named barriers 1..3: the tensor-chain token of warpgroup g
+constexpr int kBarWg = 4;                   // named barriers 4..6: warpgroup-local sync
+
+template <int C>
+struct TcCols {                             // TMEM column map of the CTA's single tile pipeline
+  static constexpr int K1 = 3 * C;
+  static constexpr int Yh = 0, Yl = K1, D1 = 2 * K1, Hl = 2 * K1 + kTcHid, D2 = 2 * K1 + 2 * kTcHid;
+  static_assert(D2 + C <= 512, "TMEM columns");
+};
+
+template <int C>
+static size_t tc_smem_bytes(int nchunks, bool graph) {
+  size_t f = (size_t)2 * kTcHid * 3 * C + (size_t)2 * C * kTcHid + kTcHid + (graph ? C * C + C : 0);
+  return f * sizeof(float) + kTcWG * 4 * 2 * sizeof(double) + kTcWG * sizeof(uint64_t) + 2 * sizeof(uint32_t) +
+         (size_t)kTcWG * (nchunks + 1) * sizeof(int) + 128;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed P, const float* __restrict__ packed,
+                                                             const uint16_t* __restrict__ glist,
+                                                             const int* __restrict__ prefix) {
+  constexpr int K1 = 3 * C;
+  using TC = TcCols<C>;
+  const int H = a.H, W = a.W, HW = H * W, nchunks = a.nchunks;
+  const bool graph = (a.flags & GNCA_F_GRAPH) != 0;
+  const int tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = tid >> 5, lane = tid & 31;
+
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+  float* sW1 = reinterpret_cast<float*>(smem_raw);              // [2][128 x 3C] canonical (hi, lo)
+  float* sW2 = sW1 + 2 * kTcHid * K1;                           // [2][C x 128]
+  float* sb1 = sW2 + 2 * C * kTcHid;
+  float* sWmT = sb1 + kTcHid;
+  float* sbm = sWmT + (graph ? C * C : 0);
+  double* sred = reinterpret_cast<double*>(sbm + (graph ? C : 0));     // [3][4][2]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sred + kTcWG * 4 * 2);  // [3]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + kTcWG);
+  int* s_pf = reinterpret_cast<int*>(tslot + 2) + g * (nchunks + 1);   // this warpgroup's prefix table
+
+  block_copy(sW1, packed + P.w1c, 2 * kTcHid * K1);
+  block_copy(sW2, packed + P.w2c, 2 * C * kTcHid);
+  block_copy(sb1, packed + P.b1, kTcHid);
+  if (graph) { block_copy(sWmT, packed + P.wmt, C * C); block_copy(sbm, packed + P.bm, C); }
+  if (warp == 0) tmem_alloc(tslot, 512);
+  if (tid == 32) {
+    for (int i = 0; i < kTcWG; ++i) mbar_init(smem_u32(mbar + i), 1);
+    mbar_init_fence();
+  }
+  fence_proxy_async();          // the weights were written through the generic proxy; the MMAs read them through the async one
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *tslot;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t tYh = tb + TC::Yh, tYl = tb + TC::Yl, tD1 = tb + TC::D1, tHl = tb + TC::Hl, tD2 = tb + TC::D2;
+  constexpr uint32_t idesc1 = idesc_tf32(128, kTcHid), idesc2 = idesc_tf32(128, C);
+  const uint32_t w1h = smem_u32(sW1), w1l = smem_u32(sW1 + kTcHid * K1);
+  const uint32_t w2h = smem_u32(sW2), w2l = smem_u32(sW2 + C * kTcHid);
+  const uint32_t my_bar = smem_u32(mbar + g);
+  uint32_t parity = 0;
+
+  const float gain_m = graph ? step_message_gain(a) : 0.f;
+  const bool do_msg = graph && gain_m != 0.f && a.k > 0;
+  const int c_lo = ((a.flags & GNCA_F_HIDDEN_ONLY) && C >= 4) ? 4 : 0;
+
+  if (g == kTcWG - 1) bar_arrive(kBarTurn + 0, 256);            // the first turn belongs to warpgroup 0
+
+  const int n_units = nchunks * a.B;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int j = unit / a.B, b = unit - j * a.B;               // j-major: the non-empty units of all samples come first
+    if (!sample_active(a, b)) continue;
+    const int* pf = prefix + (size_t)b * (nchunks + 1);
+    const int total = __ldg(pf + nchunks);
+    const int r_lo = j * kTcRange;
+    double* part = a.partials + ((size_t)b * a.npart + (size_t)j * kTcWG + g) * 2;
+    if (r_lo >= total) {
+      if (t == 0) { part[0] = 0.0; part[1] = 0.0; }
+      continue;
+    }
+    const int r_hi = min(r_lo + kTcRange, total);
+    for (int i = t; i <= nchunks; i += 128) s_pf[i] = __ldg(pf + i);
+    bar_sync(kBarWg + g, 128);
+    const float* xs_base = a.x_in + (size_t)b * C * HW;
+    float s1 = 0.f, s2 = 0.f;
+    for (int base = r_lo; base < r_hi; base += kTcThreads) {
+      const int rank = base + g * 128 + t;
+      int cell = -1;
+      if (rank < r_hi) {
+        int lo = 0, hi = nchunks;                               // s_pf[lo] <= rank < s_pf[hi]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pf[mid] <= rank) lo = mid; else hi = mid; }
+        cell = lo * kTcChunk + (int)glist[(size_t)b * HW + (size_t)lo * kTcChunk + (rank - s_pf[lo])];
+      }
+      const int cy = cell >= 0 ? cell / W : 0, cx = cell >= 0 ? cell - cy * W : 0;
+      // ---- graph message (CUDA cores; graph_augmentation.py:104-169 by linearity, ncagraph.py:94-104,141) ----------
+      float msg[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) msg[c] = 0.f;
+      if (do_msg && cell >= 0) {
+        float xsnd[C], as;
+        gather_senders<C>(a, xs_base, b, cy, cx, xsnd, as);
+        float agg[C];
+        msg_project<C>(xsnd, as, sWmT, sbm, agg);
+#pragma unroll
+        for (int c = 0; c < C; ++c) msg[c] = c >= c_lo ? tanhf(agg[c]) * gain_m : 0.f;
+      }
+      // ---- perception (perception.py:21-26) --------------------------------------------------------------------------
+      float yv[K1];
+      if (cell >= 0) {
+        perceive<C>(xs_base, cy, cx, H, W, yv);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K1; ++k) yv[k] = 0.f;
+      }
+      // ================= tensor-core chain: one warpgroup at a time ===================================================
+      bar_sync(kBarTurn + g, 256);
+      fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < K1; c0 += 16) {
+        uint32_t vh[16], vl[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) split_tf32(yv[c0 + q], vh[q], vl[q]);
+        tmem_st16(tYh + lane_base + c0, vh);
+        tmem_st16(tYl + lane_base + c0, vl);
+      }
+      wait_st();
+      fence_before();
+      bar_sync(kBarWg + g, 128);
+      if (t == 0) {                                             // layer 1: D1 = y W1^T  (update_net.0, ncagraph.py:61)
+        fence_after();
+        constexpr uint32_t sbo = (K1 / 4) * 128;
+#pragma unroll 1
+        for (int ks = 0; ks < K1 / 8; ++ks) {
+          const uint64_t bh = smem_desc(w1h + ks * 256, 128, sbo), bl = smem_desc(w1l + ks * 256, 128, sbo);
+          mma_ts(tD1, tYh + ks * 8, bh, idesc1, ks > 0);
+          mma_ts(tD1, tYh + ks * 8, bl, idesc1, 1);
+          mma_ts(tD1, tYl + ks * 8, bh, idesc1, 1);
+        }
+        mma_commit(my_bar);
+      }
+      mbar_wait(my_bar, parity); parity ^= 1;
+      fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < kTcHid; c0 += 16) {                 // epilogue 1: + b1, ReLU (update_net.1), split, back to TMEM
+        uint32_t v[16], vl[16];
+        tmem_ld16(tD1 + lane_base + c0, v);
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float h = fmaxf(__uint_as_float(v[q]) + sb1[c0 + q], 0.f);
+          split_tf32(h, v[q], vl[q]);
+        }
+        tmem_st16(tD1 + lane_base + c0, v);
+        tmem_st16(tHl + lane_base + c0, vl);
+      }
+      wait_st();
+      fence_before();
+      bar_sync(kBarWg + g, 128);
+      if (t == 0) {                                             // layer 2: D2 = h W2^T  (update_net.2, no bias)
+        fence_after();
+        constexpr uint32_t sbo = (kTcHid / 4) * 128;
+#pragma unroll 1
+        for (int ks = 0; ks < kTcHid / 8; ++ks) {
+          const uint64_t bh = smem_desc(w2h + ks * 256, 128, sbo), bl = smem_desc(w2l + ks * 256, 128, sbo);
+          mma_ts(tD2, tD1 + ks * 8, bh, idesc2, ks > 0);
+          mma_ts(tD2, tD1 + ks * 8, bl, idesc2, 1);
+          mma_ts(tD2, tHl + ks * 8, bh, idesc2, 1);
+        }
+        mma_commit(my_bar);
+      }
+      mbar_wait(my_bar, parity); parity ^= 1;
+      fence_after();
+      float dxv[C];
+#pragma unroll
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tD2 + lane_base + c0, v);
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) dxv[c0 + q] = __uint_as_float(v[q]);
+      }
+      fence_before();
+      bar_arrive(kBarTurn + (g + 1) % kTcWG, 256);              // pass the token
+      // ================================================================================================================
+      if (cell >= 0) {
+        float* up = a.u + (size_t)b * C * HW + cell;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float v = dxv[c] + msg[c];
+          up[(size_t)c * HW] = v;
+          s1 += v;
+          s2 = fmaf(v, v, s2);
+        }
+      }
+    }
+    // deterministic per-warpgroup partial of (sum u, sum u^2): fixed shuffle tree, warps added in order
+    const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
+    if (lane == 0) { sred[(g * 4 + (warp & 3)) * 2] = d1; sred[(g * 4 + (warp & 3)) * 2 + 1] = d2; }
+    bar_sync(kBarWg + g, 128);
+    if (t == 0) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int w = 0; w < 4; ++w) { t1 += sred[(g * 4 + w) * 2]; t2 += sred[(g * 4 + w) * 2 + 1]; }
+      part[0] = t1; part[1] = t2;
+    }
+  }
+  if (g == 0) bar_sync(kBarTurn + 0, 256);                      // absorb the last token
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free(tb, 512);
+}
+
+template <int C>
+static int launch_tc(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const uint16_t* glist,
+                     const int* prefix, cudaStream_t st) {
+  const bool graph = (m.flags & GNCA_F_GRAPH) != 0;
+  const size_t smem = tc_smem_bytes<C>(a.nchunks, graph);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    GNCA_CHECK_CUDA(cudaGetDevice(&dev));
+    GNCA_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int units = a.nchunks * a.B;
+  k_update_tc<C><<<units < n_sm ? units : n_sm, kTcThreads, smem, st>>>(a, P, packed, glist, prefix);
+  return 0;
+}
+
+bool update_tc_supported(const gnca_model& m, const StepArgs& a) {
+  if (!(m.C == 16 || m.C == 32) || m.hidden != kTcHid) return false;
+  if (a.chunk != kTcChunk) return false;
+  const bool graph = (m.flags & GNCA_F_GRAPH) != 0;
+  const size_t smem = m.C == 16 ? tc_smem_bytes<16>(a.nchunks, graph) : tc_smem_bytes<32>(a.nchunks, graph);
+  return smem <= 227 * 1024;
+}
+
+int launch_update_tc(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const uint16_t* glist,
+                     const int* prefix, cudaStream_t st) {
+  a.npart = kTcWG * a.nchunks;
+  if (m.C == 16) return launch_tc<16>(m, P, packed, a, glist, prefix, st);
+  return launch_tc<32>(m, P, packed, a, glist, prefix, st);
+}
+
+}  // namespace gnca

@@ -109,21 +109,58 @@ def test_rollout_grads_golden(impl, fname, kind):
 
 @pytest.mark.parametrize("impl", IMPLS)
 def test_philox_fire_stream(impl):
-    """In-kernel Philox fire masks: deterministic per seed, fire fraction ~ fire_rate, differs across seeds."""
+    """In-kernel Philox fire masks are THE stream of tests/philox_replica.py, bit for bit: a rollout that draws its
+    fire uniforms in the kernel (seed, offset) equals the same rollout fed the replica's uniforms as recorded `fire_u`
+    (same kernels, only the source of the uniforms differs -> torch.equal), for ragged step counts, per-step fire rates
+    and a non-zero stream offset.  This is the path bench.py times (fire="philox")."""
+    from philox_replica import fire_uniforms
     m = graph_model(True)
     x0 = T32(load_golden("graph_torus_step.npz")["x_in"]).to(DEV)
+    x0 = torch.cat([x0, x0.flip(0), x0], 0).contiguous()                 # B = 6
+    B, T = 6, 9
+    frs = [0.5, 0.9, 0.3, 0.7, 0.55, 0.5, 0.99, 0.1, 0.5]
+    steps = [9, 4, 0, 9, 7, 1]
+    for seed, offset in ((11, 0), (2 ** 40 + 7, 12345)):
+        random.seed(1)
+        s1 = make_schedule(m, B, 40, 40, T, fire_rate=frs, seed=seed, steps=steps)
+        s1.philox_offset = offset
+        offs = s1.offsets.cpu().numpy()
+        u = torch.from_numpy(fire_uniforms(seed, offset, T, B, 40, 40)).to(DEV)
+        s2 = make_schedule(m, B, 40, 40, T, fire_rate=frs, offsets=offs, fire_u=u, steps=steps)
+        with torch.no_grad():
+            a = _supported(impl, lambda: rollout(m, x0, s1, impl=impl))
+            b = rollout(m, x0, s2, impl=impl)
+        assert torch.equal(a, b), (impl, seed)
     random.seed(1)
-    s1 = make_schedule(m, 2, 40, 40, 5, fire_rate=0.5, seed=11)
-    random.seed(1)
-    s2 = make_schedule(m, 2, 40, 40, 5, fire_rate=0.5, seed=11)
-    random.seed(1)
-    s3 = make_schedule(m, 2, 40, 40, 5, fire_rate=0.5, seed=12)
+    s3 = make_schedule(m, B, 40, 40, T, fire_rate=frs, seed=12, steps=steps)
     with torch.no_grad():
-        a = _supported(impl, lambda: rollout(m, x0, s1, impl=impl))
-        b = rollout(m, x0, s2, impl=impl)
         c = rollout(m, x0, s3, impl=impl)
-    assert torch.equal(a, b) and not torch.equal(a, c)
-    assert torch.isfinite(a).all()
+    assert not torch.equal(a, c) and torch.isfinite(c).all()
+
+
+@pytest.mark.parametrize("impl", ["resident", "streaming"])
+def test_philox_rollout_bench_shape_vs_oracle(impl):
+    """BASELINE configs[1] exactly as bench.py runs it (B=8, T=96, 40x40x16, fire 0.5 from the in-kernel Philox stream,
+    seed growth, trained weights, torus, 8 of 72 offsets per step) against the ORACLE fed the replica's uniforms:
+    final state <= 1e-5 rel-Frobenius, alive mask bit-exact."""
+    from philox_replica import fire_uniforms
+    from oracle.nca_oracle import make_seed
+    m = graph_model(True)
+    B, T, seed = 8, 96, 4242
+    x0 = make_seed(16, 40, B)
+    random.seed(42)
+    sched = make_schedule(m, B, 40, 40, T, fire_rate=0.5, seed=seed)
+    offs = sched.offsets.cpu().numpy()
+    with torch.no_grad():
+        xT = _supported(impl, lambda: rollout(m, x0.to(DEV), sched, impl=impl))
+    u = torch.from_numpy(fire_uniforms(seed, 0, T, B, 40, 40))
+    p = load_params("weights_graph_ep960.npz")
+    with torch.no_grad():
+        ref = O.rollout(x0, p, ocfg(True), [0.5] * T, [u[t].unsqueeze(1) for t in range(T)],
+                        [tup(offs[t]) for t in range(T)])
+    assert float((ref[:, 3] > 0.12).float().mean()) > 0.05            # the pattern grew: a live test
+    assert rel_err(xT.cpu(), ref) < 1e-5, rel_err(xT.cpu(), ref)
+    assert torch.equal(GF.alive_mask(xT, 0.12).cpu(), O.alive_mask(ref, 0.12))
 
 
 def test_damage_in_rollout():
