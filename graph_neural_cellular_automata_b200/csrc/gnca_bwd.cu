@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kBThreads) k_bwd_norm(BwdArgs A, Packed P, con
     if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
       const int cell = yy * W + xx;
       act = alive_at(alpha, yy, xx, H, W, a.alpha_thr) && fires(a, fr, b, cell);
-      v = alpha[cell] + (act ? tanhf(fmaf(ub[3 * HW + cell], s_sc[3], s_bi[3])) : s_idle_th[3]) * a.update_gain;
+      v = updated_alpha(alpha[cell], act, act ? ub[3 * HW + cell] : 0.f, s_sc[3], s_bi[3],
+                        __fmul_rn(s_idle_th[3], a.update_gain), a.update_gain);
     }
     s_alpha[hy][hx] = v;
     s_act[hy][hx] = act;

@@ -205,6 +205,14 @@ __device__ __forceinline__ bool alive_at(const float* __restrict__ alpha, int y,
   return m > thr;
 }
 
+// pre-gate updated alpha x~_3 = x_3 + gain * tanh(gn(u_3)) (ncagraph.py:153-155) with EXPLICIT roundings: the streaming
+// backward recomputes it for the post-alive mask (ncagraph.py:158) and must land on the forward's bits -- a contracted
+// FMA on one side flips the mask of a cell within an ulp of the threshold (seen as a 2e-3 error of dL/dx0 of one sample
+// in the 64-step gradient fixture).  idle3 = __fmul_rn(tanhf(bi3), gain).
+__device__ __forceinline__ float updated_alpha(float alpha, bool act, float u3, float sc3, float bi3, float idle3, float gain) {
+  return __fadd_rn(alpha, act ? __fmul_rn(tanhf(fmaf(u3, sc3, bi3)), gain) : idle3);
+}
+
 // fire decision of (b, cell) at this step: (u <= fire_rate), skipped entirely when fire_rate >= 1 (ncagraph.py:144)
 __device__ __forceinline__ bool fires(const StepArgs& a, float fire_rate, int b, int cell) {
   if (fire_rate >= 1.0f) return true;

@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(kThreads) k_apply(StepArgs a, Packed P, const 
       bi = packed[P.beta + c] - s_stat[0] * sc;
     }
     s_sc[c] = sc; s_bi[c] = bi;
-    s_idle[c] = tanhf(bi) * a.update_gain;   // update of a cell whose masked pre-norm update is 0
+    s_idle[c] = __fmul_rn(tanhf(bi), a.update_gain);   // update of a cell whose masked pre-norm update is 0
   }
   __syncthreads();
 
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(kThreads) k_apply(StepArgs a, Packed P, const 
       const int cell = yy * W + xx;
       act = alive_at(alpha, yy, xx, H, W, a.alpha_thr) && fires(a, fr, b, cell);
       const float uu = act ? u3[cell] : 0.f;
-      v = alpha[cell] + (act ? tanhf(fmaf(uu, s_sc[3], s_bi[3])) * a.update_gain : s_idle[3]);
+      v = updated_alpha(alpha[cell], act, uu, s_sc[3], s_bi[3], s_idle[3], a.update_gain);
     }
     s_alpha[hy][hx] = v;
     s_act[hy][hx] = act;

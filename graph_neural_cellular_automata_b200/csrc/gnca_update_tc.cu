@@ -9,7 +9,9 @@
 //     memory;
 //   * layer 1: D1[128 cells x 128] = y W1^T as 3 x (3C/8) tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8, A from
 //     TMEM, B = the (hi, lo) split of W1 resident in shared memory in the canonical K-major layout):
-//     hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM;
+//     hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM -- the large hi*hi products and the two small cross terms in
+//     SEPARATE accumulators added in the epilogue: the tensor core truncates when it adds into an accumulator, and 36
+//     truncations at the magnitude of the result cost 3x the error of 12 (measured: scratch/umma_probe.cu);
 //   * epilogue 1 (tcgen05.ld, the thread reads ITS cell's 128 hidden units): + b1, ReLU, split, back to TMEM;
 //   * layer 2: D2[128 x C] = h W2^T the same way (N = C, K = 128); epilogue 2 adds the message and stores u.
 // Accuracy of the split (scratch/umma_probe.cu on a B200): max |err| 1.7e-6 against fp64 for outputs of magnitude ~1
@@ -19,6 +21,7 @@
 #include "gnca_common.cuh"
 #include "gnca_internal.h"
 #include "gnca_tc.cuh"
+#include <cstdio>
 
 namespace gnca {
 
@@ -34,8 +37,10 @@ constexpr int kBarWg = 4;                   // named barriers 4..6: warpgroup-lo
 template <int C>
 struct TcCols {                             // TMEM column map of the CTA's single tile pipeline
   static constexpr int K1 = 3 * C;
-  static constexpr int Yh = 0, Yl = K1, D1 = 2 * K1, Hl = 2 * K1 + kTcHid, D2 = 2 * K1 + 2 * kTcHid;
-  static_assert(D2 + C <= 512, "TMEM columns");
+  // D1 holds the hi*hi products of layer 1 and then (in place) the hi part of h; Hl holds the two small cross terms
+  // (hi*lo + lo*hi) of layer 1 and then (in place) the lo part of h; D2 / D2s the same split for layer 2.
+  static constexpr int Yh = 0, Yl = K1, D1 = 2 * K1, Hl = 2 * K1 + kTcHid, D2 = 2 * K1 + 2 * kTcHid, D2s = D2 + C;
+  static_assert(D2s + C <= 512, "TMEM columns");
 };
 
 template <int C>
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
   fence_after();
   const uint32_t tb = *tslot;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const uint32_t tYh = tb + TC::Yh, tYl = tb + TC::Yl, tD1 = tb + TC::D1, tHl = tb + TC::Hl, tD2 = tb + TC::D2;
+  const uint32_t tYh = tb + TC::Yh, tYl = tb + TC::Yl, tD1 = tb + TC::D1, tHl = tb + TC::Hl, tD2 = tb + TC::D2, tD2s = tb + TC::D2s;
   constexpr uint32_t idesc1 = idesc_tf32(128, kTcHid), idesc2 = idesc_tf32(128, C);
   const uint32_t w1h = smem_u32(sW1), w1l = smem_u32(sW1 + kTcHid * K1);
   const uint32_t w2h = smem_u32(sW2), w2l = smem_u32(sW2 + C * kTcHid);
@@ -95,6 +100,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
 
   if (g == kTcWG - 1) bar_arrive(kBarTurn + 0, 256);            // the first turn belongs to warpgroup 0
 
+#ifdef GNCA_PHASE_COUNTERS          /* development: where a tile's cycles go (thread 0 of every warpgroup of CTA 0 prints) */
+  long long ph_t = clock64(), ph[6] = {0, 0, 0, 0, 0, 0};
+  int ph_tiles = 0;
+#define TC_MARK(i) do { const long long n_ = clock64(); ph[i] += n_ - ph_t; ph_t = n_; } while (0)
+#else
+#define TC_MARK(i) do { } while (0)
+#endif
   const int n_units = nchunks * a.B;
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const int j = unit / a.B, b = unit - j * a.B;               // j-major: the non-empty units of all samples come first
@@ -121,6 +133,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
         cell = lo * kTcChunk + (int)glist[(size_t)b * HW + (size_t)lo * kTcChunk + (rank - s_pf[lo])];
       }
       const int cy = cell >= 0 ? cell / W : 0, cx = cell >= 0 ? cell - cy * W : 0;
+      TC_MARK(0);
       // ---- graph message (CUDA cores; graph_augmentation.py:104-169 by linearity, ncagraph.py:94-104,141) ----------
       float msg[C];
 #pragma unroll
@@ -133,6 +146,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
 #pragma unroll
         for (int c = 0; c < C; ++c) msg[c] = c >= c_lo ? tanhf(agg[c]) * gain_m : 0.f;
       }
+      TC_MARK(1);
       // ---- perception (perception.py:21-26) --------------------------------------------------------------------------
       float yv[K1];
       if (cell >= 0) {
@@ -142,8 +156,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
         for (int k = 0; k < K1; ++k) yv[k] = 0.f;
       }
       // ================= tensor-core chain: one warpgroup at a time ===================================================
+      TC_MARK(2);
       bar_sync(kBarTurn + g, 256);
       fence_after();
+      TC_MARK(3);
 #pragma unroll
       for (int c0 = 0; c0 < K1; c0 += 16) {
         uint32_t vh[16], vl[16];
@@ -162,8 +178,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
         for (int ks = 0; ks < K1 / 8; ++ks) {
           const uint64_t bh = smem_desc(w1h + ks * 256, 128, sbo), bl = smem_desc(w1l + ks * 256, 128, sbo);
           mma_ts(tD1, tYh + ks * 8, bh, idesc1, ks > 0);
-          mma_ts(tD1, tYh + ks * 8, bl, idesc1, 1);
-          mma_ts(tD1, tYl + ks * 8, bh, idesc1, 1);
+          mma_ts(tHl, tYh + ks * 8, bl, idesc1, ks > 0);
+          mma_ts(tHl, tYl + ks * 8, bh, idesc1, 1);
         }
         mma_commit(my_bar);
       }
@@ -173,10 +189,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
       for (int c0 = 0; c0 < kTcHid; c0 += 16) {                 // epilogue 1: + b1, ReLU (update_net.1), split, back to TMEM
         uint32_t v[16], vl[16];
         tmem_ld16(tD1 + lane_base + c0, v);
+        tmem_ld16(tHl + lane_base + c0, vl);
         wait_ld();
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          const float h = fmaxf(__uint_as_float(v[q]) + sb1[c0 + q], 0.f);
+          const float h = fmaxf((__uint_as_float(v[q]) + __uint_as_float(vl[q])) + sb1[c0 + q], 0.f);
           split_tf32(h, v[q], vl[q]);
         }
         tmem_st16(tD1 + lane_base + c0, v);
@@ -192,8 +209,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
         for (int ks = 0; ks < kTcHid / 8; ++ks) {
           const uint64_t bh = smem_desc(w2h + ks * 256, 128, sbo), bl = smem_desc(w2l + ks * 256, 128, sbo);
           mma_ts(tD2, tD1 + ks * 8, bh, idesc2, ks > 0);
-          mma_ts(tD2, tD1 + ks * 8, bl, idesc2, 1);
-          mma_ts(tD2, tHl + ks * 8, bh, idesc2, 1);
+          mma_ts(tD2s, tD1 + ks * 8, bl, idesc2, ks > 0);
+          mma_ts(tD2s, tHl + ks * 8, bh, idesc2, 1);
         }
         mma_commit(my_bar);
       }
@@ -202,14 +219,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
       float dxv[C];
 #pragma unroll
       for (int c0 = 0; c0 < C; c0 += 16) {
-        uint32_t v[16];
+        uint32_t v[16], vs[16];
         tmem_ld16(tD2 + lane_base + c0, v);
+        tmem_ld16(tD2s + lane_base + c0, vs);
         wait_ld();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) dxv[c0 + q] = __uint_as_float(v[q]);
+        for (int q = 0; q < 16; ++q) dxv[c0 + q] = __uint_as_float(v[q]) + __uint_as_float(vs[q]);
       }
       fence_before();
       bar_arrive(kBarTurn + (g + 1) % kTcWG, 256);              // pass the token
+      TC_MARK(4);
       // ================================================================================================================
       if (cell >= 0) {
         float* up = a.u + (size_t)b * C * HW + cell;
@@ -221,6 +240,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
           s2 = fmaf(v, v, s2);
         }
       }
+      TC_MARK(5);
+#ifdef GNCA_PHASE_COUNTERS
+      ++ph_tiles;
+#endif
     }
     // deterministic per-warpgroup partial of (sum u, sum u^2): fixed shuffle tree, warps added in order
     const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
@@ -232,6 +255,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
       part[0] = t1; part[1] = t2;
     }
   }
+#ifdef GNCA_PHASE_COUNTERS
+  if (blockIdx.x == 0 && t == 0 && a.t == 2 && ph_tiles > 0)
+    printf("[k_update_tc phases, CTA 0 warpgroup %d, %d tiles] per tile: lookup %lld  message %lld  perception %lld  wait-turn %lld  "
+           "tensor chain %lld  store %lld cycles\n", g, ph_tiles, ph[0] / ph_tiles, ph[1] / ph_tiles, ph[2] / ph_tiles,
+           ph[3] / ph_tiles, ph[4] / ph_tiles, ph[5] / ph_tiles);
+#endif
+#undef TC_MARK
   if (g == 0) bar_sync(kBarTurn + 0, 256);                      // absorb the last token
   fence_before();
   __syncthreads();

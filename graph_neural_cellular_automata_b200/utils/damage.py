@@ -26,6 +26,11 @@ def _apply(state: torch.Tensor, D: torch.Tensor) -> None:
     _lib.check(_lib.load().gnca_apply_mask(state.numel(), GF._ptr(state), GF._ptr(D), GF._stream()), "gnca_apply_mask")
 
 
+def dense_mask(D: torch.Tensor, state: torch.Tensor) -> torch.Tensor:
+    """The [B,C,H,W] multiplicative mask a builder's (broadcastable) result stands for."""
+    return D.expand_as(state).contiguous()
+
+
 def _grid(state):
     B, Cc, H, W = state.shape
     yy = torch.arange(H, device=state.device).view(1, H, 1)
@@ -147,11 +152,9 @@ def hidden_scramble_(state, sigma=0.2):
     state[:, 4:] = (state[:, 4:] + noise).clamp_(0.0, 1.0)
 
 
-@torch.no_grad()
-def sample_damage_mask(state, dmg_cfg, epoch):
-    """The policy of apply_damage_policy_ (damage.py:101-138) returning the mask instead of applying it
-    (None = no damage this batch).  Draw order: torch.rand(1) gate, random.choices(kind), random.randint(size),
-    then the kind's own draws."""
+def _draw_policy(state, dmg_cfg, epoch):
+    """The batch-level draws of apply_damage_policy_ (damage.py:101-121), in the reference's order: torch.rand(1) gate,
+    random.choices(kind), random.randint(size).  Returns (kind, size) or None (no damage this batch)."""
     start_ep = int(dmg_cfg.get("start_epoch", dmg_cfg.get("damage_start_epoch", 100)))
     prob = float(dmg_cfg.get("prob", dmg_cfg.get("damage_prob", 0.0)))
     if epoch < start_ep or prob <= 0:
@@ -163,7 +166,11 @@ def sample_damage_mask(state, dmg_cfg, epoch):
     kind = random.choices(names, weights=weights, k=1)[0]
     size_min = int(dmg_cfg.get("size_min", dmg_cfg.get("damage_patch_size", 8)))
     size_max = int(dmg_cfg.get("size_max", max(size_min, 14)))
-    size = int(random.randint(size_min, size_max))
+    return kind, int(random.randint(size_min, size_max))
+
+
+def _policy_mask(state, dmg_cfg, kind, size):
+    """Mask of the drawn (kind, size) with the kind's own geometry draws (damage.py:122-138); None = nothing to apply."""
     if kind == "circle":
         r = size // 2 if size > 1 else 1
         return circle_mask(state, r) if r > 0 else None
@@ -178,14 +185,29 @@ def sample_damage_mask(state, dmg_cfg, epoch):
         return salt_pepper_mask(state, p) if p > 0 else None
     if kind == "gaussian":
         return gaussian_mask(state, max(1, size // 2), float(dmg_cfg.get("gaussian_softness", 0.35)))
-    if kind == "hidden_noise":
-        hidden_scramble_(state, float(dmg_cfg.get("hidden_noise_sigma", 0.0)))
-        return None
     return square_mask(state, size) if size > 0 else None      # "square" and the reference's fallback
 
 
 @torch.no_grad()
+def sample_damage_mask(state, dmg_cfg, epoch):
+    """The policy of apply_damage_policy_ (damage.py:101-138) returning the multiplicative mask instead of applying it
+    (None = no damage this batch).  PURE: `state` is only read (shape, device, alpha for alpha_drop).  The additive
+    `hidden_noise` kind (weight 0 / absent in the default policy) has no mask: it yields None here and is applied by
+    apply_damage_policy_."""
+    drawn = _draw_policy(state, dmg_cfg, epoch)
+    if drawn is None or drawn[0] == "hidden_noise":
+        return None
+    return _policy_mask(state, dmg_cfg, *drawn)
+
+
+@torch.no_grad()
 def apply_damage_policy_(state, dmg_cfg, epoch):
-    D = sample_damage_mask(state, dmg_cfg, epoch)
+    drawn = _draw_policy(state, dmg_cfg, epoch)
+    if drawn is None:
+        return
+    if drawn[0] == "hidden_noise":
+        hidden_scramble_(state, float(dmg_cfg.get("hidden_noise_sigma", 0.0)))
+        return
+    D = _policy_mask(state, dmg_cfg, *drawn)
     if D is not None:
         _apply(state, D)

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) k_single(const float* __restrict__ A /*[1
 template <int C>
 __global__ void __launch_bounds__(128) k_mlp(const float* __restrict__ Y /*[128][96]*/, const float* __restrict__ W1c /*[2][128*96]*/,
                                              const float* __restrict__ b1, const float* __restrict__ W2c /*[2][C*128]*/,
-                                             float* __restrict__ out /*[grid][128][C]*/, int reps, long long* __restrict__ cycles) {
+                                             float* __restrict__ out /*[grid][128][C]*/, int reps, long long* __restrict__ cycles, int split_acc) {
   extern __shared__ __align__(1024) unsigned char smem[];
   float* sW1 = reinterpret_cast<float*>(smem);       // hi, lo
   float* sW2 = sW1 + 2 * N1 * K1;                    // hi, lo
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(128) k_mlp(const float* __restrict__ Y /*[128]
   tc_fence_after();
   const uint32_t tb = tmem_base_s;
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  // columns: Y hi [0,96) lo [96,192); D1 -> H hi [192,320); H lo [320,448); D2 [448,448+C)
-  const uint32_t tYh = tb, tYl = tb + 96, tD1 = tb + 192, tHl = tb + 320, tD2 = tb + 448;
+  // columns: Y hi [0,96) lo [96,192); D1 -> H hi [192,320); cross terms -> H lo [320,448); D2 [448,448+C); D2 cross [448+C,448+2C)
+  const uint32_t tYh = tb, tYl = tb + 96, tD1 = tb + 192, tHl = tb + 320, tD2 = tb + 448, tD2s = tb + 448 + C;
   const uint32_t idesc1 = make_idesc_tf32(M, N1), idesc2 = make_idesc_tf32(M, C);
   uint32_t parity = 0;
   float yreg[K1];
@@ -196,8 +196,13 @@ __global__ void __launch_bounds__(128) k_mlp(const float* __restrict__ Y /*[128]
       const uint32_t w1h = smem_u32(sW1), w1l = smem_u32(sW1 + N1 * K1);
       for (int ks = 0; ks < K1 / 8; ++ks) {
         mma_ts(tD1, tYh + ks * 8, make_desc(w1h + ks * 256, 128, sbo), idesc1, ks > 0);
-        mma_ts(tD1, tYh + ks * 8, make_desc(w1l + ks * 256, 128, sbo), idesc1, 1);
-        mma_ts(tD1, tYl + ks * 8, make_desc(w1h + ks * 256, 128, sbo), idesc1, 1);
+        if (split_acc) {
+          mma_ts(tHl, tYh + ks * 8, make_desc(w1l + ks * 256, 128, sbo), idesc1, ks > 0);
+          mma_ts(tHl, tYl + ks * 8, make_desc(w1h + ks * 256, 128, sbo), idesc1, 1);
+        } else {
+          mma_ts(tD1, tYh + ks * 8, make_desc(w1l + ks * 256, 128, sbo), idesc1, 1);
+          mma_ts(tD1, tYl + ks * 8, make_desc(w1h + ks * 256, 128, sbo), idesc1, 1);
+        }
       }
       mma_commit(smem_u32(&bar));
     }
@@ -208,10 +213,11 @@ __global__ void __launch_bounds__(128) k_mlp(const float* __restrict__ Y /*[128]
     for (int c0 = 0; c0 < N1; c0 += 16) {
       uint32_t v[16], vl[16];
       tmem_ld16(tD1 + lane_base + c0, v);
+      if (split_acc) tmem_ld16(tHl + lane_base + c0, vl);
       tc_wait_ld();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float h = fmaxf(__uint_as_float(v[j]) + sb1[c0 + j], 0.f);
+        const float h = fmaxf((__uint_as_float(v[j]) + (split_acc ? __uint_as_float(vl[j]) : 0.f)) + sb1[c0 + j], 0.f);
         split_tf32(h, v[j], vl[j]);
       }
       tmem_st16(tD1 + lane_base + c0, v);
@@ -226,8 +232,13 @@ __global__ void __launch_bounds__(128) k_mlp(const float* __restrict__ Y /*[128]
       const uint32_t w2h = smem_u32(sW2), w2l = smem_u32(sW2 + C * N1);
       for (int ks = 0; ks < N1 / 8; ++ks) {
         mma_ts(tD2, tD1 + ks * 8, make_desc(w2h + ks * 256, 128, sbo), idesc2, ks > 0);
-        mma_ts(tD2, tD1 + ks * 8, make_desc(w2l + ks * 256, 128, sbo), idesc2, 1);
-        mma_ts(tD2, tHl + ks * 8, make_desc(w2h + ks * 256, 128, sbo), idesc2, 1);
+        if (split_acc) {
+          mma_ts(tD2s, tD1 + ks * 8, make_desc(w2l + ks * 256, 128, sbo), idesc2, ks > 0);
+          mma_ts(tD2s, tHl + ks * 8, make_desc(w2h + ks * 256, 128, sbo), idesc2, 1);
+        } else {
+          mma_ts(tD2, tD1 + ks * 8, make_desc(w2l + ks * 256, 128, sbo), idesc2, 1);
+          mma_ts(tD2, tHl + ks * 8, make_desc(w2h + ks * 256, 128, sbo), idesc2, 1);
+        }
       }
       mma_commit(smem_u32(&bar));
     }
@@ -235,11 +246,12 @@ __global__ void __launch_bounds__(128) k_mlp(const float* __restrict__ Y /*[128]
     tc_fence_after();
 #pragma unroll
     for (int c0 = 0; c0 < C; c0 += 16) {
-      uint32_t v[16];
+      uint32_t v[16], vs[16];
       tmem_ld16(tD2 + lane_base + c0, v);
+      if (split_acc) tmem_ld16(tD2s + lane_base + c0, vs);
       tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) dx[c0 + j] = __uint_as_float(v[j]);
+      for (int j = 0; j < 16; ++j) dx[c0 + j] = __uint_as_float(v[j]) + (split_acc ? __uint_as_float(vs[j]) : 0.f);
     }
     // keep the loop honest: the next tile's input depends on this tile's output (by a negligible amount)
     yreg[0] += dx[0] * 1e-30f;
@@ -257,7 +269,7 @@ static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xffffe00
 static float tf32_rna_host(float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x1000u; u &= 0xffffe000u; float r; memcpy(&r, &u, 4); return r; }
 
 template <int C>
-static void run_mlp(const std::vector<float>& Y, const std::vector<float>& W1, const std::vector<float>& b1, int nsm) {
+static void run_mlp(const std::vector<float>& Y, const std::vector<float>& W1, const std::vector<float>& b1, int nsm, int split_acc) {
   std::vector<float> W2((size_t)C * N1);
   srand(7 + C);
   for (auto& v : W2) v = ((rand() / (float)RAND_MAX) - 0.5f) * 0.2f;
@@ -277,7 +289,7 @@ static void run_mlp(const std::vector<float>& Y, const std::vector<float>& W1, c
   CK(cudaMemcpy(db1, b1.data(), b1.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dW2c, W2c.data(), W2c.size() * 4, cudaMemcpyHostToDevice));
   const size_t smem = (size_t)(2 * N1 * K1 + 2 * C * N1 + N1) * 4;
   CK(cudaFuncSetAttribute(k_mlp<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_mlp<C><<<1, 128, smem>>>(dY, dW1c, db1, dW2c, dout, 1, nullptr);
+  k_mlp<C><<<1, 128, smem>>>(dY, dW1c, db1, dW2c, dout, 1, nullptr, split_acc);
   CK(cudaDeviceSynchronize());
   std::vector<float> out((size_t)M * C);
   CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
@@ -295,13 +307,13 @@ static void run_mlp(const std::vector<float>& Y, const std::vector<float>& W1, c
       emax = fmax(emax, fabs(out[r * C + c] - s)); e32max = fmax(e32max, fabs((double)sf - s)); refmax = fmax(refmax, fabs(s));
     }
   }
-  printf("T3 C=%d  3xTF32 MLP: max|err| vs fp64 = %.3e (fp32 FFMA chain: %.3e), max|ref| = %.3e -> rel %.3e\n", C, emax, e32max, refmax, emax / refmax);
+  printf("T3 C=%d split_acc=%d  3xTF32 MLP: max|err| vs fp64 = %.3e (fp32 FFMA chain: %.3e), max|ref| = %.3e -> rel %.3e\n", C, split_acc, emax, e32max, refmax, emax / refmax);
   // throughput: every SM, reps tiles
   const int reps = 2000;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  k_mlp<C><<<nsm, 128, smem>>>(dY, dW1c, db1, dW2c, dout, 50, dcyc);
+  k_mlp<C><<<nsm, 128, smem>>>(dY, dW1c, db1, dW2c, dout, 50, dcyc, split_acc);
   CK(cudaEventRecord(e0));
-  k_mlp<C><<<nsm, 128, smem>>>(dY, dW1c, db1, dW2c, dout, reps, dcyc);
+  k_mlp<C><<<nsm, 128, smem>>>(dY, dW1c, db1, dW2c, dout, reps, dcyc, split_acc);
   CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
   std::vector<long long> cyc(nsm); CK(cudaMemcpy(cyc.data(), dcyc, nsm * 8, cudaMemcpyDeviceToHost));
@@ -347,8 +359,10 @@ int main() {
     printf("T%d %s  max|D - exact| = %.3e   max|D - tf32(trunc) ref| = %.3e   max|D - tf32(rna) ref| = %.3e   (max|ref| %.3e)\n",
            ts + 1, ts ? "TS" : "SS", e_full, e_trunc, e_rna, rmax);
   }
-  run_mlp<32>(A, B, b1, prop.multiProcessorCount);
-  run_mlp<16>(A, B, b1, prop.multiProcessorCount);
+  for (int sa = 0; sa < 2; ++sa) {
+    run_mlp<32>(A, B, b1, prop.multiProcessorCount, sa);
+    run_mlp<16>(A, B, b1, prop.multiProcessorCount, sa);
+  }
   printf("done\n");
   return 0;
 }

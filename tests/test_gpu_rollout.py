@@ -15,7 +15,7 @@ if torch.cuda.is_available():
     import graph_neural_cellular_automata_b200 as G
     from graph_neural_cellular_automata_b200 import functional as GF
     from graph_neural_cellular_automata_b200.rollout import make_schedule, rollout
-    from test_gpu_step import graph_model, classic_model, T32, tup, DEV
+    from test_gpu_step import graph_model, classic_model, ocfg, T32, tup, DEV
 
 IMPLS = ["streaming", "resident", "banded"]
 

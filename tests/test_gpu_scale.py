@@ -50,12 +50,14 @@ def test_one_step_vs_oracle_at_scale():
     chosen = random.sample(m.graph.offsets, 8)
     cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=True, message_gain=0.3, hidden_only=True,
                        zero_padded_shift=False)
-    ref = O.nca_step(x, p, cfg, 0.5, fu, chosen)
+    # fp64 oracle: deterministic, and the accuracy yard-stick of SURVEY 8c-ii (the fp32 CPU oracle's own distance to it
+    # varies run to run at this size with the thread count of the box)
+    ref = O.nca_step(x.double(), {k: v.double() for k, v in p.items()}, cfg, 0.5, fu.double(), chosen)
     with torch.no_grad():
         out = m.step(x.to(DEV), 0.5, fire_u=fu.to(DEV), chosen=chosen)
     assert max_rel(out.cpu(), ref) < 1e-5, max_rel(out.cpu(), ref)           # 1e-5 relative, single step (north star)
     assert rel_err(out.cpu(), ref) < 1e-5
-    assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref, 0.1))  # alive mask bit-exact
+    assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))  # alive mask bit-exact
 
 
 def test_rollout_properties_at_scale():

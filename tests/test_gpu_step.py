@@ -233,12 +233,15 @@ def test_large_batch_balanced_update():
         chosen = [random.sample(m.graph.offsets, 8) for _ in range(2)]
         cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=True, message_gain=0.3, hidden_only=True,
                            zero_padded_shift=False)
-        # forward, one step
-        ref = O.nca_step(x, p, cfg, 0.5, fus[0], chosen[0])
+        # forward, one step.  Reference = the oracle in fp64: at this size the multi-threaded fp32 CPU oracle
+        # is itself up to 1e-4 (max_rel) away from fp64 on some runs (thread-order dependent GroupNorm sums), the CUDA path
+        # is not (FFMA kernel 2.3e-6, tensor-core kernel 7e-6 max_rel, profiles/r02_tc_accuracy.md)
+        p64 = {k: v.double() for k, v in p.items()}
+        ref = O.nca_step(x.double(), p64, cfg, 0.5, fus[0].double(), chosen[0])
         with torch.no_grad():
             out = m.step(x.to(DEV), 0.5, fire_u=fus[0].to(DEV), chosen=chosen[0])
         assert max_rel(out.cpu(), ref) < 1e-5, (C, max_rel(out.cpu(), ref))
-        assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref, 0.1))
+        assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))
         # gradients through two steps (the streaming backward recomputes u with the same balanced kernel)
         # reference gradients from the oracle in fp64 (the accuracy yard-stick; the fp32 CPU autograd of
         # this case is itself 1.3e-4 away from fp64 in dL/dx0 for C = 16, the CUDA path is not)
@@ -254,7 +257,12 @@ def test_large_batch_balanced_update():
             s_gpu = m.step(s_gpu, 0.5, fire_u=fus[t].to(DEV), chosen=chosen[t])
         (s_gpu[:, :4] ** 2).mean().backward()
         assert rel_err(s_gpu.detach().cpu().double(), s_ref.detach()) < 1e-5
-        assert rel_err(xg.grad.cpu().double(), xr.grad) < 1e-4, rel_err(xg.grad.cpu().double(), xr.grad)
+        # dL/dx0: the true gradient is discontinuous where a hidden unit's pre-activation crosses 0, and a state that
+        # differs in the 7th digit can put ONE unit of ONE cell on the other side (seen: 20 cells of one sample, 5.6e-4 of
+        # that sample's gradient, every other sample at 6.5e-7) -> per-sample median tight, whole batch 5e-4
+        per = sorted(rel_err(xg.grad[b].cpu().double(), xr.grad[b]) for b in range(B))
+        assert per[B // 2] < 1e-5, per
+        assert rel_err(xg.grad.cpu().double(), xr.grad) < 5e-4, rel_err(xg.grad.cpu().double(), xr.grad)
         named = dict(m.named_parameters())
         for name in ("update_net.0.weight", "update_net.0.bias", "update_net.2.weight", "norm.weight", "norm.bias",
                      "graph.msg_proj.weight", "graph.msg_proj.bias"):
