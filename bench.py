@@ -8,14 +8,21 @@ growth from the single-cell seed.  A "step" of this bench = ONE such rollout (B*
   value : rollouts timed with CUDA events, x0 / weights / schedule resident in HBM, L2 flushed between iterations.
   e2e   : the same through the public API with HOST buffers: pinned x0 -> H2D, schedule draws (random.sample per
           step, as T forward calls would), rollout, x_T -> D2H.  Wall clock around each call (sync both sides).
-  roofline      : dominant kernel, CUDA events around its launches (library hook), fp32-FMA bound.
-  cpu_baseline  : oracle/ port of the reference's PyTorch path on the host cores (N=1, rank 0).
-  --impl reference : the oracle port alone, same JSON shape.
+  roofline      : dominant kernel, CUDA events around its launches (library hook), fp32-FMA bound; ncu-derived fields
+                  (DRAM traffic, pipe utilisation) are read from the tracked capture summary profiles/ncu_r02.json.
+  cpu_baseline  : the REFERENCE's own modules (oracle/_ref, staged by oracle/build_ref.py; oracle port if absent) on
+                  the host cores (N=1, rank 0);  gpu_eager: the same modules in PyTorch eager on the B200.
+  fwd_bwd       : BASELINE configs[2]/[3] through the public trainer API (GraphNCATrainer.train_step: pool draw, damage
+                  policy, per-sample randint step counts, per-step U(0.5,0.9) fire rate, msg_every=3, loss, BPTT,
+                  NCCL all-reduce, normalise + Adam, worst-k reseed, pool replace), short and long regime separately,
+                  weak (32 per GPU) and -- for N > 1 -- strong (global batch 32) scaling; its own roofline, cpu_baseline
+                  and gpu_eager.
+  --impl reference : the reference modules alone on the host cores, same JSON shape, batch scaled with --gpus.
 
-Other workloads: --workload c1 (classic NCA rollout), c3 (training step fwd+bwd, B=32, T=64: also part of the default
-line as `fwd_bwd`), c4 (c3 with an in-kernel damage mask),
-c3l (the same at T=300, long regime), c5s (256x256x32 scale-up slice, streaming kernels), c5 (the full per-GPU share of
-BASELINE configs[4]: B=128, T=1000, damage at t=500 -- seconds per rollout: run it with --steps 2 --warmup 1).
+Other workloads: --workload c1 (classic NCA rollout), c3 / c3l (the training HOT PATH only -- rollout fwd+bwd, loss,
+optimiser -- at fixed T=64 / T=300, no pool: a kernel-development line), c4 (c3 with an in-kernel damage mask), c5s
+(256x256x32 scale-up slice, streaming kernels), c5 (the full per-GPU share of BASELINE configs[4]: B=128, T=1000,
+damage at t=500 -- seconds per rollout: run it with --steps 2 --warmup 1).
 """
 from __future__ import annotations
 
@@ -40,12 +47,30 @@ FLOP_FWD_GRAPH_S = 17.9e3
 FLOP_FWDBWD_GRAPH_S = 53.6e3
 FLOP_FWD_GRAPH_L = 36.7e3
 FP32_LANES = 148 * 128 * 2           # FMA lanes x 2 flop
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_DRAM_BYTES = {("c2", "k_rep_fwd"): 1090816,     # profiles/r01_rep_fwd_summary.md: 1.090304 MB read, 0 written (x_T still in L2)
-                  ("c5", "k_update"): 112492544}    # profiles/r01_k_update_summary.md (B=16 slice): 81.27 MB read + 31.22 MB written
-# sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active of the same captures: the REAL pipe utilisation next to the
-# dense-equivalent fraction (which counts the flops of the cells the kernels skip)
-NCU_FMA_PIPE_PCT = {("c2", "k_rep_fwd"): 18.5, ("c3", "k_rep_bwd"): 30.1, ("c5", "k_update"): 31.8}
+
+
+def load_peaks():
+    """Measured roofline denominators (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]), "source": "MEASURED_PEAKS.json (of measured)"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+PEAKS = load_peaks()
+
+
+def ncu_capture(workload, kernel):
+    """ncu-derived facts of (workload, kernel) from the tracked summary profiles/ncu_r02.json (written by
+    scripts/ncu_summary.py from a committed `ncu --set full` capture; each entry names its command, report and commit).
+    They describe THAT capture, not this run -- the bench line says so next to the numbers."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_r02.json")) as f:
+            return json.load(f).get(f"{workload}:{kernel}")
+    except Exception:
+        return None
 
 
 def load_weights(name):
@@ -123,78 +148,114 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def build_oracle_inputs(cfg, seed=42):
-    """Deterministic draws for the CPU port: offsets per step + fire uniforms."""
-    from oracle import nca_oracle as O
-    random.seed(seed)
-    torch.manual_seed(seed)
-    offs = O.build_offsets(4)
-    chosens = [random.sample(offs, 8) for _ in range(cfg["T"])]
-    return chosens
-
-
-def cpu_port_rollout(cfg, params, T, chosens):
-    """The reference's PyTorch path restated (oracle/), CPU, no grad: T forward calls from the seed."""
-    from oracle import nca_oracle as O
-    oc = O.StepConfig(update_gain=0.05, alpha_thr=0.12, graph=True, message_gain=0.25, hidden_only=True,
-                      zero_padded_shift=False)
-    x = O.make_seed(cfg["C"], cfg["H"], cfg["B"])
-    with torch.no_grad():
-        for t in range(T):
-            fu = torch.rand(cfg["B"], 1, cfg["H"], cfg["W"])
-            c = oc
-            if cfg["message_every"] > 1 and t % cfg["message_every"] != 0:
-                c = O.StepConfig(**{**oc.__dict__, "message_gain": 0.0})
-            x = O.nca_step(x, params, c, cfg["fire_rate"], fu, chosens[t])
-    return x
-
-
-def time_cpu_port(cfg, reps=2):
-    params = load_weights("weights_graph_ep960.npz")
-    if cfg["C"] != 16:
+def cpu_forward_baseline(cfg):
+    """cpu_baseline of a forward workload: the reference's modules on all host cores, full workload, best of 2."""
+    import bench_ref
+    if cfg["C"] != 16 or cfg.get("classic"):
         return None
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    chosens = build_oracle_inputs(cfg)
-    T = cfg["T"]
-    cpu_port_rollout(cfg, params, min(T, 8), chosens)           # warm-up
-    best = float("inf")
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        cpu_port_rollout(cfg, params, T, chosens)
-        best = min(best, time.perf_counter() - t0)
-    updates = cfg["B"] * T * cfg["H"] * cfg["W"]
-    return {"value": updates / best, "unit": "cell-updates/s", "cores": threads, "kind": "port",
-            "sample": f"full workload: B={cfg['B']} T={T} {cfg['H']}x{cfg['W']}x{cfg['C']} forward rollout, best of {reps}, "
-                      f"{best:.2f} s per rollout, torch CPU {torch.__version__}"}
+    r = bench_ref.time_forward(cfg["B"], cfg["T"], cfg["fire_rate"], "cpu", reps=2)
+    return {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"], "kind": r["kind"],
+            "sample": f"full workload: B={cfg['B']} T={cfg['T']} {cfg['H']}x{cfg['W']}x{cfg['C']} forward rollout, best of 2, "
+                      f"{r['seconds']:.2f} s per rollout, torch CPU {torch.__version__}"}
+
+
+def gpu_eager_forward(cfg, dev):
+    """The reference's modules in PyTorch eager ON THE B200 (like-for-like GPU comparator)."""
+    import bench_ref
+    if cfg["C"] != 16 or cfg.get("classic"):
+        return None
+    r = bench_ref.time_forward(cfg["B"], cfg["T"], cfg["fire_rate"], dev, reps=3)
+    return {"value": r["value"], "unit": "cell-updates/s", "kind": r["kind"] + " modules, torch eager on cuda",
+            "ms_per_step": r["seconds"] * 1e3, "sample": f"full workload, best of 3, torch {torch.__version__}"}
 
 
 def run_reference_arm(args, cfg, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores, on OUR arm's
+    config (weak scaling: per-GPU batch x --gpus), rank 0 only."""
     if rank != 0:
         return
-    params = load_weights("weights_graph_ep960.npz")
+    import bench_ref
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    chosens = build_oracle_inputs(cfg)
+    B = cfg["B"] * max(1, args.gpus)
+    model, kind = bench_ref.make_reference_graph("cpu")
+    random.seed(42); torch.manual_seed(42)
     T = cfg["T"]
     for _ in range(args.warmup):
-        cpu_port_rollout(cfg, params, T, chosens)
+        bench_ref.forward_rollout(model, B, T, cfg["fire_rate"], "cpu", cfg["message_every"])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_port_rollout(cfg, params, T, chosens)
+        bench_ref.forward_rollout(model, B, T, cfg["fire_rate"], "cpu", cfg["message_every"])
     dt = time.perf_counter() - t0
-    updates = cfg["B"] * T * cfg["H"] * cfg["W"]
+    updates = B * T * cfg["H"] * cfg["W"]
     val = updates * args.steps / dt
     line = {"impl": "reference", "metric": "graph-NCA cell-updates/s (fwd)", "value": val, "unit": "cell-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "B": cfg["B"], "T": T, "grid": [cfg["H"], cfg["W"]], "channels": cfg["C"],
-                       "note": "reference's PyTorch CPU path restated in oracle/ (the reference checkout does not travel)"},
-            "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": threads, "kind": "port",
-                             "sample": "full workload per step"},
+            "config": {"workload": cfg["name"], "B_per_gpu": cfg["B"], "B_total": B, "T": T, "grid": [cfg["H"], cfg["W"]],
+                       "channels": cfg["C"],
+                       "note": "the reference's own modules (oracle/_ref, staged from /root/reference/src by "
+                               "oracle/build_ref.py) on the host cores; oracle port when that directory is absent"},
+            "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": threads, "kind": kind,
+                             "sample": f"full workload per step (B={B} = {cfg['B']} per GPU x {max(1, args.gpus)})"},
             "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def make_roofline(cfg, kname, ms, n, nprof, updates, clocks, kernels_ms, step_ms, x_numel, T, args, active_frac=None):
+    """roofline object of the dominant kernel `kname` (ms over n launches in nprof steps of `updates` cell-updates).
+    FFMA kernels (k_rep_*, the FFMA k_update): fp32-FMA bound, dense-equivalent flops.  The tensor-core k_update
+    (256x256x32 path): its 3xTF32 MMAs are far from the tensor peak, the step is bound by moving the state -> HBM view
+    (8C bytes per cell and step for the streaming pair) with the tensor view beside it."""
+    wl = cfg["name"][:2]
+    # algorithmic (dense) flops / launch.  Training step: the credited 3 x forward flops split evenly over its three
+    # kernels (forward 17.9 k; data gradients gh, gy, perception^T, message^T 17.9 k; weight gradients 17.8 k per
+    # cell-update -- the hidden-layer recompute inside k_rep_bwd is overhead and not credited, SURVEY 8d)
+    kflop = cfg["flop"] / 3.0 if cfg["train"] else cfg["flop"]
+    flops_per_launch = kflop * updates * nprof / n
+    avg_s = ms * 1e-3 / n
+    mhz = clocks["sm_max_mhz"] or 1965
+    peak32 = FP32_LANES * mhz * 1e6 / 1e12
+    ach32 = flops_per_launch / avg_s / 1e12
+    cap = ncu_capture(wl, kname) or {}
+    cap_note = (f"ncu fields from the committed capture {cap.get('report')} ({cap.get('command')}, commit {cap.get('commit')}); "
+                "they describe that capture, not this run") if cap else "no committed ncu capture for this kernel / workload"
+    streaming = kname in ("k_update", "k_apply")
+    state_bytes = x_numel * 4
+    hbm = {"algorithmic_bytes_per_step": int(2 * state_bytes * (T if streaming else 1)),
+           "achieved_GBps": 2 * state_bytes * (T if streaming else 1) * nprof / (ms * 1e-3) / 1e9, "peak_GBps": PEAKS["hbm_gbs"]}
+    common = {"kernel": kname, "avg_launch_ms": avg_s * 1e3, "launches_per_step": n / nprof,
+              "share_of_step": ms / nprof / step_ms, "kernels": kernels_ms,
+              "traffic": cap.get("dram_bytes_per_launch"), "ncu": {k: v for k, v in cap.items() if k.endswith("_pct")},
+              "ncu_source": cap_note}
+    tc = streaming and cfg["C"] in (16, 32) and cfg["hidden"] == 128 and not os.environ.get("GNCA_NO_TC") and \
+        cfg["B"] * ((cfg["H"] * cfg["W"] + 1023) // 1024) >= 2 * 148
+    if tc and kname == "k_update":
+        # k_update_tc per launch: reads x of the step once (the 3x3 / sender re-reads are L2 hits by design), writes u of the
+        # active cells; the MLP runs as 3 TF32 passes on the tensor cores
+        af = active_frac if active_frac is not None else cap.get("active_fraction", 0.28)
+        bytes_launch = state_bytes * (1.0 + af)
+        ach = bytes_launch / avg_s / 1e9
+        mlp_flop = 2.0 * (3 * cfg["C"] * cfg["hidden"] + cfg["hidden"] * cfg["C"])
+        tf32_exec = 3.0 * mlp_flop * af * (updates / T) / avg_s / 1e12
+        return {"bound": "hbm", "achieved": ach, "peak": PEAKS["hbm_gbs"], "unit": "GB/s", "frac": ach / PEAKS["hbm_gbs"],
+                "peak_source": PEAKS["source"],
+                "note": "algorithmic bytes of ONE k_update_tc launch (state read once + u of the active cells written, active "
+                        f"fraction {af:.2f}) / its CUDA-event duration; the launch also covers k_compact + k_scan",
+                "tensor_view": {"executed_tf32_TFLOPs": tf32_exec, "peak_tf32_TFLOPs": PEAKS["bf16_tflops"] / 2,
+                                "frac": tf32_exec / (PEAKS["bf16_tflops"] / 2),
+                                "note": "3 TF32 passes x 2*(3C*hid + hid*C) flops x ACTIVE cells; tf32 dense peak taken as half "
+                                        "the measured bf16 cuBLAS figure"},
+                "fp32_dense_equivalent": {"achieved_TFLOPs": ach32, "ffma_peak_TFLOPs": peak32, "frac": ach32 / peak32},
+                "step_hbm_view": hbm, **common}
+    return {"bound": "fp32_fma", "achieved": ach32, "peak": peak32, "unit": "TFLOP/s", "frac": ach32 / peak32,
+            "peak_source": f"derived: 148 SM x 128 FMA lanes x 2 x {mhz} MHz (MEASURED_PEAKS.json has no fp32 entry; "
+                           f"hbm_gbs {PEAKS['hbm_gbs']} measured is far from binding: see hbm_view)",
+            "note": "achieved = DENSE algorithmic flops (every cell counted) / measured kernel time; the kernel "
+                    "skips cells whose fire*alive mask is 0, so frac is a dense-equivalent figure (the ncu pipe "
+                    "utilisation of the committed capture is in `ncu`)",
+            "hbm_view": hbm, **common}
 
 
 def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_roofline=True):
@@ -368,31 +429,128 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
         if per_kernel:
             kname = max(per_kernel, key=lambda k: per_kernel[k][0])
             ms, n = per_kernel[kname]
-            # algorithmic (dense) flops / launch.  Training step: the credited 3 x forward flops split evenly over its three
-            # kernels (forward 17.9 k; data gradients gh, gy, perception^T, message^T 17.9 k; weight gradients 17.8 k per
-            # cell-update -- the hidden-layer recompute inside k_rep_bwd is overhead and not credited)
-            kflop = cfg["flop"] / 3.0 if cfg["train"] else cfg["flop"]
-            flops_per_launch = kflop * updates * nprof / n
-            avg_s = ms * 1e-3 / n
-            clocks = sampler.result()
-            mhz = clocks["sm_max_mhz"] or 1965
-            peak = FP32_LANES * mhz * 1e6 / 1e12
-            achieved = flops_per_launch / avg_s / 1e12
-            roof = {"bound": "fp32_fma", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": NCU_DRAM_BYTES.get((cfg["name"][:2], kname)) if (cfg["name"][:2] != "c5" or B == 16) else None,
-                    "fma_pipe_pct_ncu": NCU_FMA_PIPE_PCT.get((cfg["name"][:2], kname)), "avg_launch_ms": avg_s * 1e3, "launches_per_step": n / nprof,
-                    "peak_source": f"derived: 148 SM x 128 FMA lanes x 2 x {mhz} MHz (MEASURED_PEAKS.json has no fp32 entry; "
-                                   "hbm_gbs 6547.8 measured is far from binding: see hbm_view)",
-                    "note": "achieved = DENSE algorithmic flops (every cell counted) / measured kernel time; the kernel "
-                            "skips cells whose fire*alive mask is 0, so frac is a dense-equivalent figure",
-                    # resident kernel: x_0 in + x_T out per rollout; streaming step kernels: state in + out per CA step
-                    "hbm_view": {"algorithmic_bytes_per_step": int(2 * x0_host.numel() * 4 * (T if kname in ("k_update", "k_apply") else 1)),
-                                 "achieved_GBps": 2 * x0_host.numel() * 4 * (T if kname in ("k_update", "k_apply") else 1) * nprof / (ms * 1e-3) / 1e9,
-                                 "peak_GBps": 6547.8},
-                    "share_of_step": ms / nprof / (dev_ms_max / steps), "kernels": kernels_ms}
+            roof = make_roofline(cfg, kname, ms, n, nprof, updates, sampler.result(), kernels_ms, dev_ms_max / steps,
+                                 x0_host.numel(), T, args)
 
     return {"value": value, "ms_per_step": dev_ms_max / steps, "e2e": e2e, "launches": int(launches), "roofline": roof,
             "clocks": sampler.result(), "data": data, "dims": (C_, H, W, B, T)}
+
+
+def run_trainer(args, world, rank, local_rank, dev, steps, warmup, regime="short", scaling="weak", per_gpu=32,
+                damage=False):
+    """BASELINE configs[2] / [3]: the training iteration through the PUBLIC trainer API (GraphNCATrainer.train_step,
+    the loop body of train_graph_augmented_nca.py:289-391): pool draw (1024-pool of mixed ages), damage policy
+    (configs[3]: the reference's config.json `damage` section at epoch >= 100), per-sample randint step counts
+    (short [48,80] / long [200,400]), per-step U(0.5,0.9) fire rate, message on t % 3 == 0, in-kernel Philox fire masks,
+    loss, BPTT, NCCL all-reduce of the flat gradient, normalise + Adam, all-gather of losses / states, worst-k reseed,
+    pool replace.  weak: `per_gpu` samples per GPU; strong: global batch `per_gpu` split over the ranks."""
+    import ctypes
+    import torch.distributed as dist
+    import graph_neural_cellular_automata_b200 as G
+    from graph_neural_cellular_automata_b200 import _lib
+    from graph_neural_cellular_automata_b200.rollout import make_schedule, rollout
+    from graph_neural_cellular_automata_b200.training.trainer import GraphNCATrainer, TrainConfig
+
+    lib = _lib.load()
+    Bg = per_gpu * world if scaling == "weak" else per_gpu
+    if Bg % world:
+        return None
+    torch.manual_seed(1234); random.seed(1234)           # every rank replays the SAME host RNG (training/dp.py)
+    model = G.NeuralCAGraph(16, update_hidden=128, img_size=40, update_gain=0.05, alpha_thr=0.12, message_gain=0.25,
+                            hidden_only=True, graph_zero_padded_shift=False)
+    model.load_state_dict(load_weights("weights_graph_ep960.npz"), strict=False)
+    model = model.to(dev)
+    target = torch.from_numpy(np.load(os.path.join(GOLDEN, "target_gecko_surrogate.npy"))).to(dev)
+    dmg = {}
+    if damage:           # /root/reference/configs/config.json `damage` with prob 1 so that every timed step carries the mask
+        dmg = {"start_epoch": 100, "prob": 1.0, "kinds": {"square": 0.35, "circle": 0.25, "stripes": 0.1, "alpha_drop": 0.15,
+               "saltpepper": 0.05, "gaussian": 0.1}, "size_min": 6, "size_max": 18, "stripe_width": 6, "alpha_thr": 0.2,
+               "alpha_dropout_p": 0.15, "salt_pepper_p": 0.02, "gaussian_softness": 0.35}
+    tcfg = TrainConfig(batch_size=Bg, pool_size=1024, long_rollout_prob=1.0 if regime == "long" else 0.0, fire="philox",
+                       rollout_impl=args.rollout_impl, damage=dmg)
+    tr = GraphNCATrainer(model, target, tcfg)
+    # pool of mixed ages (SURVEY 8d C3): every slot rolled 0..160 steps from its seed, no grad
+    with torch.no_grad():
+        for i0 in range(0, 1024, 256):
+            ages = [random.randint(0, 160) for _ in range(256)]
+            sched = make_schedule(model, 256, 40, 40, max(ages), fire_rate=0.6, steps=ages, fire="philox", seed=77 + i0)
+            tr.pool.pool[i0:i0 + 256] = rollout(model, tr.pool.pool[i0:i0 + 256].contiguous(), sched)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    for _ in range(warmup):
+        tr.train_step(epoch=300)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = lib.gnca_launch_count()
+    evs, updates, steps_sum = [], 0, 0
+    for i in range(steps):
+        flush.fill_(float(i))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = tr.train_step(epoch=300)
+        e1.record()
+        evs.append((e0, e1))
+        updates += out["cell_updates"]; steps_sum += int(out["steps"].max())
+    torch.cuda.synchronize()
+    launches = lib.gnca_launch_count() - launches0
+    sampler.stop_flag = True; sampler.join()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    # end to end: the same call + the device->host read of the step's result (the loss) inside the wall-clock region
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    upd2 = 0
+    for i in range(steps):
+        out = tr.train_step(epoch=300)
+        loss = float(out["loss"])                      # D2H of the step's result
+        upd2 += out["cell_updates"]
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    Tavg = steps_sum / steps
+    e2e = {"value": upd2 / e2e_s, "unit": "cell-updates/s", "ms_per_step": e2e_s / steps * 1e3,
+           "h2d_bytes_per_step": int(Tavg * 24 + Bg // world * 4), "d2h_bytes_per_step": int(Bg * 8 + 4),
+           "note": "train_step() + float(loss); the pool lives on the device as in the reference (pool.py keeps device tensors)"}
+    # per-kernel device time (library event hook)
+    lib.gnca_profile_enable(1)
+    nprof = min(steps, 5)
+    upd3 = 0
+    for i in range(nprof):
+        upd3 += tr.train_step(epoch=300)["cell_updates"]
+    torch.cuda.synchronize()
+    lib.gnca_profile_enable(0)
+    per_kernel = {}
+    for kid, kname in ((0, "k_update"), (1, "k_apply"), (2, "k_rep_fwd"), (3, "k_rep_wgrad"), (6, "k_rep_bwd")):
+        ms, n = ctypes.c_double(0), ctypes.c_ulonglong(0)
+        lib.gnca_profile_read(kid, ctypes.byref(ms), ctypes.byref(n))
+        if n.value:
+            per_kernel[kname] = (ms.value, n.value)
+    kernels_ms = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof} for k, v in per_kernel.items()}
+    roof = None
+    if per_kernel:
+        kname = max(per_kernel, key=lambda k: per_kernel[k][0])
+        ms, n = per_kernel[kname]
+        cfg3 = {"name": "c3", "train": True, "flop": FLOP_FWDBWD_GRAPH_S, "C": 16, "H": 40, "W": 40, "hidden": 128, "B": Bg // world}
+        roof = make_roofline(cfg3, kname, ms, n, nprof, upd3 / world / nprof, sampler.result(), kernels_ms, dev_ms / steps,
+                             Bg // world * 16 * 1600, int(Tavg), args)
+    return {"metric": "graph-NCA cell-updates/s (fwd+bwd)", "value": updates / (dev_ms * 1e-3), "unit": "cell-updates/s",
+            "ms_per_step": dev_ms / steps, "n_gpus": world, "scaling": scaling, "regime": regime, "e2e": e2e,
+            "gpu_launches": int(launches), "steps_timed": steps, "mean_T": Tavg, "clocks": sampler.result(),
+            "config": {"workload": "configs[%d]: GraphNCATrainer.train_step, %s regime%s" % (3 if damage else 2, regime,
+                                                                                           ", damage policy on every step" if damage else ""),
+                       "global_batch": Bg, "B_per_gpu": Bg // world, "pool": 1024, "steps": "randint(48,80)" if regime == "short" else "randint(200,400)",
+                       "fire_rate": "U(0.5,0.9) per step", "message_every": 3, "fire_rng": "in-kernel philox (per-rank stream offset)",
+                       "parallelism": f"dp{world}: batch sharded, NCCL all-reduce of the 9,169-float gradient + all-gather of losses / final states"},
+            "roofline": roof}
 
 
 def main():
@@ -433,21 +591,30 @@ def main():
     C_, H, W, B, T = res["dims"]
     value, e2e, launches, roof, data = res["value"], res["e2e"], res["launches"], res["roofline"], res["data"]
 
-    # the other half of the metric ("fwd, fwd+bwd"): the training hot path (fwd with BPTT records, loss, resident
-    # backward, batched weight gradients, all-reduce, normalise + Adam) on BASELINE configs[2]'s shape, short regime
+    # the other half of the metric ("fwd, fwd+bwd"): BASELINE configs[2] (and, for N > 1, configs[3]) through the trainer
     train = None
     if args.workload == "c2" and not args.no_train_extra:
-        cfg3 = workload_cfg("c3")
-        r3 = run_workload(cfg3, args, world, rank, local_rank, dev, max(3, min(args.steps, 10)), 3, with_roofline=True)
-        train = {"metric": "graph-NCA cell-updates/s (fwd+bwd)", "value": r3["value"], "unit": "cell-updates/s",
-                 "ms_per_step": r3["ms_per_step"], "e2e": r3["e2e"], "gpu_launches": r3["launches"],
-                 "config": {"workload": cfg3["name"], "B_per_gpu": cfg3["B"], "T": cfg3["T"], "fire_rate": cfg3["fire_rate"],
-                            "message_every": cfg3["message_every"]},
-                 "kernels": (r3["roofline"] or {}).get("kernels")}
+        ts = max(3, min(args.steps, 10))
+        train = {"short": run_trainer(args, world, rank, local_rank, dev, ts, 3, "short", "weak"),
+                 "long": run_trainer(args, world, rank, local_rank, dev, 3, 3, "long", "weak")}
+        if world > 1:    # configs[3]: damage curriculum, global batch 32 sharded 16 / 8 / 4 per GPU (strong) and 32 per GPU (weak)
+            train["damage_weak"] = run_trainer(args, world, rank, local_rank, dev, ts, 3, "short", "weak", damage=True)
+            train["damage_strong"] = run_trainer(args, world, rank, local_rank, dev, ts, 3, "short", "strong", damage=True)
+        else:
+            train["damage_weak"] = run_trainer(args, world, rank, local_rank, dev, ts, 3, "short", "weak", damage=True)
 
-    cpu = None
+    cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not cfg["train"] and not cfg.get("classic"):
-        cpu = time_cpu_port(cfg)
+        cpu = cpu_forward_baseline(cfg)
+        eager = gpu_eager_forward(cfg, dev)
+        if train is not None:
+            import bench_ref
+            r = bench_ref.time_train_step("cpu", batch=32, steps=1)
+            train["cpu_baseline"] = {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"], "kind": r["kind"],
+                                     "sample": r["sample"] + f"; {r['seconds_per_step']:.1f} s"}
+            r = bench_ref.time_train_step(dev, batch=32, steps=3, warmup=1)
+            train["gpu_eager"] = {"value": r["value"], "unit": "cell-updates/s", "kind": r["kind"] + " modules + torch.optim.Adam, torch eager on cuda",
+                                  "ms_per_step": r["seconds_per_step"] * 1e3, "sample": r["sample"]}
 
     if rank == 0:
         line = {"metric": "graph-NCA cell-updates/s (%s)" % ("fwd+bwd" if cfg["train"] else "fwd"), "value": value,
@@ -459,7 +626,7 @@ def main():
                            "graph_shift": "torus", "fire_rng": "in-kernel philox", "rollout_impl": args.rollout_impl,
                            "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": f"dp{world} batch-sharded, no collective"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": res["clocks"], "roofline": roof,
-                "cpu_baseline": cpu, "fwd_bwd": train}
+                "cpu_baseline": cpu, "gpu_eager": eager, "fwd_bwd": train}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -22,29 +22,6 @@ def build_offsets(radius: int) -> List[Tuple[int, int]]:
     return [(dy, dx) for dy in span for dx in span if max(abs(dy), abs(dx)) >= 2]
 
 
-_FAST_SAMPLE_CACHE = {}
-
-
-def _native_sample(n: int, k: int, T: int):
-    """T x random.sample(range(n), k) by the C host function gnca_host_sample_indices on the interpreter's MT19937
-    state (get/setstate around it): the same stream as T random.sample calls at ~1/10 of the python cost."""
-    import ctypes as C
-    import numpy as np
-    from .. import _lib
-    lib = _lib.load()
-    ver, internal, gauss = random.getstate()
-    st = np.array(internal, dtype=np.uint32)
-    mti = np.array([int(st[624])], dtype=np.int32)
-    out = np.empty(T * k, dtype=np.int32)
-    rc = lib.gnca_host_sample_indices(st.ctypes.data_as(C.c_void_p), mti.ctypes.data_as(C.c_void_p), n, k, T,
-                                      out.ctypes.data_as(C.c_void_p))
-    if rc != 0:
-        raise RuntimeError("gnca_host_sample_indices failed")
-    st[624] = mti[0]
-    random.setstate((ver, tuple(st.tolist()), gauss))
-    return out
-
-
 def _words_sample(table, n: int, k: int, T: int):
     """T x random.sample(offsets, k) as an int8 [T,k,2] array: a block of raw MT19937 outputs is pulled with ONE
     random.getrandbits call, the C host function gnca_host_sample_offsets_words replays random.sample on it and says
@@ -72,7 +49,6 @@ def _words_sample(table, n: int, k: int, T: int):
     return out
 
 
-_NATIVE_SAMPLE_CACHE = {}
 _WORDS_SAMPLE_CACHE = {}
 
 
@@ -97,56 +73,6 @@ def _words_sample_ok(offsets, n: int, k: int) -> bool:
             random.setstate(state)
         _WORDS_SAMPLE_CACHE[key] = ok
     return _WORDS_SAMPLE_CACHE[key]
-
-
-def _native_sample_ok(n: int, k: int) -> bool:
-    """One-time self-check per (n, k): the native replay must reproduce random.sample AND leave the same state."""
-    key = (n, k)
-    if key not in _NATIVE_SAMPLE_CACHE:
-        ok = False
-        state = random.getstate()
-        try:
-            if state[0] == 3 and len(state[1]) == 625:
-                ref = [random.sample(range(n), k) for _ in range(5)]
-                after_ref = random.getstate()
-                random.setstate(state)
-                mine = _native_sample(n, k, 5).reshape(5, k).tolist()
-                ok = mine == ref and random.getstate() == after_ref
-        except Exception:
-            ok = False
-        finally:
-            random.setstate(state)
-        _NATIVE_SAMPLE_CACHE[key] = ok
-    return _NATIVE_SAMPLE_CACHE[key]
-
-
-def _fast_sample_ok(n: int, k: int) -> bool:
-    """True iff replaying random.sample's pool algorithm with random._randbelow reproduces random.sample(range(n), k)
-    (checked once per (n, k) on a saved/restored RNG state)."""
-    key = (n, k)
-    if key not in _FAST_SAMPLE_CACHE:
-        ok = False
-        try:
-            state = random.getstate()
-            try:
-                ref = [random.sample(range(n), k) for _ in range(3)]
-                random.setstate(state)
-                rb = random._randbelow
-                mine = []
-                for _ in range(3):
-                    pool, res = list(range(n)), []
-                    for i in range(k):
-                        j = rb(n - i)
-                        res.append(pool[j])
-                        pool[j] = pool[n - i - 1]
-                    mine.append(res)
-                ok = mine == ref
-            finally:
-                random.setstate(state)
-        except Exception:
-            ok = False
-        _FAST_SAMPLE_CACHE[key] = ok
-    return _FAST_SAMPLE_CACHE[key]
 
 
 class GraphAugmentation(nn.Module):
@@ -179,11 +105,10 @@ class GraphAugmentation(nn.Module):
         return random.sample(self.offsets, k) if k > 0 else []
 
     def draw_offsets_array(self, T: int):
-        """T consecutive `draw_offsets()` results as one int8 array [T,k,2] -- the SAME python-RNG stream as T
-        forward calls, drawn without per-step tuple/list churn (the rollout's host-side schedule construction).
-        `random.sample` on a short sequence is a partial Fisher-Yates over a copy of the population driven by
-        `random._randbelow`; that loop is replayed here on indices.  A one-time self-check against
-        `random.sample` guards the private-API assumption and falls back to plain `random.sample` if it fails."""
+        """T consecutive `draw_offsets()` results as one int8 array [T,k,2] -- the SAME python-RNG stream as T forward
+        calls.  Fast path: one block of raw MT19937 outputs replayed by the C host function (`_words_sample`, guarded by
+        a one-time self-check against `random.sample` including the state it leaves behind); otherwise plain
+        `random.sample` per step."""
         import numpy as np
         n, k = len(self.offsets), min(self.num_neighbors, len(self.offsets))
         table = getattr(self, "_offset_table", None)
@@ -193,21 +118,8 @@ class GraphAugmentation(nn.Module):
             return np.zeros((T, 0, 2), np.int8)
         if T >= 4 and _words_sample_ok(self.offsets, n, k):
             return _words_sample(table, n, k, T)
-        if T >= 4 and _native_sample_ok(n, k):
-            idx = _native_sample(n, k, T)
-        elif _fast_sample_ok(n, k):
-            rb = random._randbelow
-            idx = []
-            for _ in range(T):
-                pool = list(range(n))
-                for i in range(k):
-                    j = rb(n - i)
-                    idx.append(pool[j])
-                    pool[j] = pool[n - i - 1]
-        else:
-            pos = {o: i for i, o in enumerate(self.offsets)}
-            idx = [pos[o] for _ in range(T) for o in random.sample(self.offsets, k)]
-        return table[np.asarray(idx, dtype=np.intp)].reshape(T, k, 2)
+        flat = [v for _ in range(T) for o in random.sample(self.offsets, k) for v in o]
+        return np.asarray(flat, dtype=np.int8).reshape(T, k, 2)
 
     def forward(self, x: torch.Tensor, return_attention_map: bool = False):
         from .. import graph_ops

@@ -29,15 +29,29 @@ class Shard:
         return t[self.lo:self.hi]
 
     # -- collectives --------------------------------------------------------------------------------------
+    def _host_staged(self, t: torch.Tensor) -> bool:
+        """gloo has no CUDA transport here: CUDA tensors go through the host (the single-GPU DP equivalence test runs two
+        ranks on one device with gloo; on the box the backend is NCCL and nothing is staged)."""
+        return t.is_cuda and dist.get_backend() == "gloo"
+
     def allreduce_sum_(self, flat: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            if self._host_staged(flat):
+                h = flat.cpu()
+                dist.all_reduce(h, op=dist.ReduceOp.SUM)
+                flat.copy_(h)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         return flat
 
     def allgather(self, local: torch.Tensor) -> torch.Tensor:
         """[local_batch, ...] -> [global_batch, ...] in rank order."""
         if self.world == 1:
             return local
+        if self._host_staged(local):
+            parts = [torch.empty(local.shape, dtype=local.dtype) for _ in range(self.world)]
+            dist.all_gather(parts, local.cpu().contiguous())
+            return torch.cat(parts, 0).to(local.device)
         out = torch.empty((self.global_batch,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous())
         return out

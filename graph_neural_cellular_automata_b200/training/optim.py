@@ -62,9 +62,12 @@ class FusedNormalizedAdam:
         self.model.invalidate_packed()
 
     # ---- torch.optim.Adam-format state (what the reference's checkpoints hold: train...:405-416) -------------------
-    def torch_state_dict(self):
+    def torch_state_dict(self, current_lr: Optional[float] = None):
         """State in `torch.optim.Adam(model.parameters()).state_dict()` format (indices = position in
-        `model.parameters()`), so a checkpoint written here resumes in the reference's trainer and vice versa."""
+        `model.parameters()`), so a checkpoint written here resumes in the reference's trainer and vice versa.
+        `current_lr`: the learning rate the scheduler holds NOW (the trainer passes the decayed rate per step and never
+        stores it here).  torch's StepLR is chainable: after a resume it multiplies `group["lr"]`, it does not recompute
+        it from `base_lrs`, so the group must carry the decayed value and `initial_lr` the base one."""
         params = list(self.model.parameters())
         index = {id(p): i for i, p in enumerate(params)}
         state = {}
@@ -76,7 +79,8 @@ class FusedNormalizedAdam:
                 state[index[id(p)]] = {"step": torch.tensor(float(self.step_count)),
                                        "exp_avg": self.exp_avg[sl].view(p.shape).clone(),
                                        "exp_avg_sq": self.exp_avg_sq[sl].view(p.shape).clone()}
-        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+        group = {"lr": float(self.lr if current_lr is None else current_lr), "initial_lr": float(self.lr),
+                 "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
                  "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
                  "fused": None, "params": list(range(len(params)))}
         return {"state": state, "param_groups": [group]}
@@ -86,7 +90,7 @@ class FusedNormalizedAdam:
         params = list(self.model.parameters())
         index = {id(p): i for i, p in enumerate(params)}
         g = sd["param_groups"][0]
-        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        self.lr, self.betas, self.eps = float(g.get("initial_lr", g["lr"])), tuple(g["betas"]), float(g["eps"])
         self.weight_decay = float(g["weight_decay"])
         self.exp_avg.zero_(); self.exp_avg_sq.zero_()
         step = 0

@@ -143,6 +143,10 @@ class GraphNCATrainer:
                               fire="philox", seed=random.getrandbits(63) if cfg.fire == "philox" else 0,
                               device=dev)
         sched.fire_rate = fr_dev                                            # device-resident draws, no .item()
+        if cfg.fire == "philox" and sh.world > 1:
+            # the in-kernel counter is indexed by the LOCAL sample (t*B_local + b): give every rank its own block range so
+            # that the fire masks of the global batch are independent, like the reference's one torch.rand over the batch
+            sched.philox_offset = sh.rank * ((T * sh.local_batch * H * W + 3) // 4)
         if fire_u is not None:
             sched.fire_u = fire_u[:, sh.lo:sh.hi].contiguous().view(T, sh.local_batch, H, W)
         return sched, steps_host

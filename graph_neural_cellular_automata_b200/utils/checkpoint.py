@@ -26,7 +26,12 @@ def steplr_state(base_lr: float, step_size: int, gamma: float, last_epoch: int) 
 
 def save_checkpoint(path: str, model, optimizer, epoch: int, global_step: Optional[int] = None, config=None,
                     scheduler_state: Optional[dict] = None) -> dict:
-    opt_state = optimizer.torch_state_dict() if hasattr(optimizer, "torch_state_dict") else optimizer.state_dict()
+    if hasattr(optimizer, "torch_state_dict"):
+        # group["lr"] = what the scheduler holds at this epoch (decayed), group["initial_lr"] = the base rate
+        cur = scheduler_state["_last_lr"][0] if scheduler_state and scheduler_state.get("_last_lr") else None
+        opt_state = optimizer.torch_state_dict(current_lr=cur)
+    else:
+        opt_state = optimizer.state_dict()
     payload = {"epoch": int(epoch), "model_state": {k: v.detach().cpu() for k, v in model.state_dict().items()},
                "optimizer_state": opt_state, "scheduler_state": scheduler_state, "config": config,
                "param_count": sum(p.numel() for p in model.parameters() if p.requires_grad),

@@ -54,13 +54,43 @@ def test_optimizer_state_round_trips_through_torch_adam(tmp_path):
     sch.load_state_dict(payload["scheduler_state"])
 
 
+def test_resume_in_stock_adam_steplr_after_a_decay_boundary(tmp_path):
+    """A checkpoint written here AFTER the first StepLR boundary resumes in the reference's trainer (stock Adam + StepLR,
+    train_graph_augmented_nca.py:143-158,405-416) at the DECAYED rate: StepLR is chainable and continues from
+    `param_groups[0]["lr"]`, so the payload must carry base*gamma**(last_epoch//step_size) there, `initial_lr` = base."""
+    base, step_size, gamma = 2e-4, 150, 0.85
+    m = _model()
+    opt = FusedNormalizedAdam(m, lr=base, weight_decay=1e-5)
+    opt.exp_avg.normal_(); opt.exp_avg_sq.uniform_(); opt.step_count = 5
+    for last_epoch in (149, 150, 301, 449):
+        path = str(tmp_path / f"nca_epoch{last_epoch}.pt")
+        CK.save_checkpoint(path, m, opt, epoch=last_epoch, scheduler_state=CK.steplr_state(base, step_size, gamma, last_epoch))
+        payload = torch.load(path, map_location="cpu", weights_only=False)
+        ref_opt = torch.optim.Adam(_model().parameters(), lr=base, weight_decay=1e-5)
+        ref_sch = torch.optim.lr_scheduler.StepLR(ref_opt, step_size=step_size, gamma=gamma)
+        ref_opt.load_state_dict(payload["optimizer_state"])
+        ref_sch.load_state_dict(payload["scheduler_state"])
+        want = base * gamma ** (last_epoch // step_size)
+        assert ref_opt.param_groups[0]["lr"] == pytest.approx(want, rel=1e-12)
+        assert ref_opt.param_groups[0]["initial_lr"] == base
+        ref_opt.step(); ref_sch.step()                         # one more epoch in the reference's loop
+        assert ref_opt.param_groups[0]["lr"] == pytest.approx(base * gamma ** ((last_epoch + 1) // step_size), rel=1e-12)
+        # and back: the base rate, not the decayed one, is what this optimiser keeps (the trainer decays per step)
+        opt2 = FusedNormalizedAdam(_model(), lr=1.0)
+        opt2.load_torch_state_dict(payload["optimizer_state"])
+        assert opt2.lr == base
+
+
 @pytest.mark.skipif(not os.path.exists(REF_CKPT), reason="needs the reference checkout (build container only)")
 def test_shipped_reference_checkpoint_resumes():
     m = _model()
     opt = FusedNormalizedAdam(m, lr=1.0)
     payload, missing, unexpected = CK.load_checkpoint(REF_CKPT, m, opt)
     assert not missing and not unexpected and payload["epoch"] == 960
-    assert opt.step_count > 0 and abs(opt.lr - payload["optimizer_state"]["param_groups"][0]["lr"]) < 1e-12
+    # the shipped payload carries the DECAYED rate in "lr" (1.4e-7 at epoch 960) and the base one in "initial_lr" (5e-4):
+    # this optimiser keeps the base rate, the trainer derives the decayed one per step (lr_at)
+    grp = payload["optimizer_state"]["param_groups"][0]
+    assert opt.step_count > 0 and opt.lr == grp["initial_lr"] and grp["lr"] < grp["initial_lr"]
     ref_state = payload["optimizer_state"]["state"][1]                  # update_net.0.weight
     sl = slice(opt.seg[0], opt.seg[1])
     assert torch.equal(opt.exp_avg[sl].view(128, 48, 1, 1), ref_state["exp_avg"])

@@ -127,12 +127,11 @@ def test_pool_semantics():
 
 
 def test_native_offset_sampling_is_the_python_stream():
-    """gnca_host_sample_indices (C, MT19937 replay) == T x random.sample(graph.offsets, k), state included."""
+    """draw_offsets_array (C block replay of MT19937 outputs) == T x random.sample(graph.offsets, k), state included."""
     import random
     import graph_neural_cellular_automata_b200 as G
     from graph_neural_cellular_automata_b200.modules import graph_augmentation as GA
     m = G.NeuralCAGraph(16, update_hidden=128, img_size=40, graph_zero_padded_shift=False)
-    assert GA._native_sample_ok(len(m.graph.offsets), 8)
     assert GA._words_sample_ok(m.graph.offsets, len(m.graph.offsets), 8)      # the block replay draw_offsets_array uses
     for seed, T in ((0, 4), (7, 96), (123, 400)):
         random.seed(seed)
