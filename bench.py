@@ -333,7 +333,7 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
     dmg = None
     if cfg.get("damage"):      # one damage kind / size for the batch, per-sample positions (utils/damage.py), applied in-kernel at step 0
         from graph_neural_cellular_automata_b200.utils.damage import circle_mask
-        dmg = circle_mask(x0_dev, int(cfg.get("damage_size", 5))).expand_as(x0_dev).contiguous()
+        dmg = circle_mask(x0_dev, int(cfg.get("damage_size", 5)))      # a Damage descriptor -> per-cell plane, no [B,C,H,W] mask
 
     def new_schedule(seed):
         return make_schedule(model, B, H, W, T, fire_rate=cfg["fire_rate"], message_every=cfg["message_every"],

@@ -31,12 +31,21 @@ class GncaSchedule(C.Structure):
     _fields_ = [("T", C.c_int32), ("k", C.c_int32), ("fire_rate", C.c_void_p), ("message_gain", C.c_void_p),
                 ("offsets", C.c_void_p), ("steps", C.c_void_p), ("fire_u", C.c_void_p),
                 ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("damage", C.c_void_p),
-                ("damage_step", C.c_int32), ("max_offset", C.c_int32)]
+                ("damage_step", C.c_int32), ("max_offset", C.c_int32), ("damage_layout", C.c_int32),
+                ("reserved_", C.c_int32)]
+
+
+class GncaDamage(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("size", C.c_int32), ("softness", C.c_float), ("p", C.c_float),
+                ("alpha_thr", C.c_float), ("reserved_", C.c_int32), ("pos", C.c_void_p), ("rand", C.c_void_p)]
 
 
 EXPORTS = {
     # name: (restype, argtypes)
     "gnca_version": (C.c_int, []),
+    "gnca_damage_plane": (C.c_int, [C.POINTER(GncaDamage), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_int32), C.c_void_p]),
+    "gnca_apply_plane": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "gnca_error_string": (C.c_char_p, [C.c_int]),
     "gnca_launch_count": (C.c_ulonglong, []),
     "gnca_profile_enable": (C.c_int, [C.c_int]),

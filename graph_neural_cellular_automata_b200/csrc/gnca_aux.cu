@@ -151,6 +151,54 @@ inline int grid_for(size_t n, int threads = 256) {
   return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// damage descriptor -> per-cell plane (utils/damage.py:16-98 in closed form; one thread per cell)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_damage_plane(gnca_damage d, int B, int C, int H, int W, const float* __restrict__ state,
+                               float* __restrict__ plane) {
+  const int HW = H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * HW) return;
+  const int b = (int)(i / HW), cell = (int)(i - (size_t)b * HW), y = cell / W, x = cell - y * W;
+  float v = 1.f;
+  switch (d.kind) {
+    case GNCA_DK_SQUARE: {                       // state[b, :, y0:y0+size, x0:x0+size] = 0       damage.py:16-24
+      const long long y0 = d.pos[2 * b], x0 = d.pos[2 * b + 1];
+      if (y >= y0 && y < y0 + d.size && x >= x0 && x < x0 + d.size) v = 0.f;
+    } break;
+    case GNCA_DK_CIRCLE: {                       // (yy-cy)^2 + (xx-cx)^2 <= r^2 -> 0              damage.py:27-37
+      const long long dy = y - d.pos[2 * b], dx = x - d.pos[2 * b + 1];
+      if (dy * dy + dx * dx <= (long long)d.size * d.size) v = 0.f;
+    } break;
+    case GNCA_DK_STRIPE_H: { const long long s0 = d.pos[0]; if (y >= s0 && y < s0 + d.size) v = 0.f; } break;   // :40-51
+    case GNCA_DK_STRIPE_V: { const long long s0 = d.pos[0]; if (x >= s0 && x < s0 + d.size) v = 0.f; } break;
+    case GNCA_DK_GAUSSIAN: {                     // clamp(1 - exp(-r2 / (2 (R*soft)^2)), 0, 1)      damage.py:87-98
+      const long long dy = y - d.pos[2 * b], dx = x - d.pos[2 * b + 1];
+      const float r2 = (float)(dy * dy + dx * dx);
+      const float sg = (float)d.size * fmaxf(1e-6f, d.softness);
+      const float m = expf(-(r2 / (2.0f * sg * sg)));
+      v = fminf(fmaxf(1.0f - m, 0.f), 1.f);
+    } break;
+    case GNCA_DK_ALPHA_DROP:                     // (rand < p) * (alpha > thr) -> 0, all channels   damage.py:54-66
+      if (d.rand[i] < d.p && state[((size_t)b * C + 3) * HW + cell] > d.alpha_thr) v = 0.f;
+      break;
+    case GNCA_DK_SALTPEPPER:                     // rand < p -> alpha 0                             damage.py:69-73
+      if (d.rand[i] < d.p) v = 0.f;
+      break;
+  }
+  plane[i] = v;
+}
+
+__global__ void k_apply_plane(int B, int C, int HW, float* __restrict__ x, const float* __restrict__ plane, int alpha_only) {
+  const size_t n = (size_t)B * C * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t bc = i / HW;
+    const int c = (int)(bc % C);
+    if (alpha_only && c != 3) continue;
+    x[i] *= plane[(bc / C) * HW + (i - bc * HW)];
+  }
+}
 }  // namespace gnca
 
 using namespace gnca;
@@ -207,6 +255,30 @@ int gnca_normalize_adam(float* params_dev, float* grads_dev, float* exp_avg_dev,
 int gnca_apply_mask(int64_t n, float* x_dev, const float* mask_dev, void* stream) {
   if (!x_dev || !mask_dev || n <= 0) return GNCA_ERR_ARG;
   k_apply_mask<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(n, x_dev, mask_dev);
+  GNCA_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnca_damage_plane(const gnca_damage* d, int B, int C, int H, int W, const float* state_dev, float* plane_dev,
+                      int32_t* layout_out, void* stream) {
+  if (!d || !plane_dev || B <= 0 || C <= 0 || H <= 0 || W <= 0) return GNCA_ERR_ARG;
+  if (d->kind < GNCA_DK_SQUARE || d->kind > GNCA_DK_SALTPEPPER) return GNCA_ERR_UNSUPPORTED;
+  const bool needs_pos = d->kind <= GNCA_DK_GAUSSIAN, needs_rand = d->kind >= GNCA_DK_ALPHA_DROP;
+  if ((needs_pos && !d->pos) || (needs_rand && !d->rand)) return GNCA_ERR_ARG;
+  if (d->kind == GNCA_DK_ALPHA_DROP && (!state_dev || C < 4)) return GNCA_ERR_ARG;
+  const size_t n = (size_t)B * H * W;
+  k_damage_plane<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*d, B, C, H, W, state_dev, plane_dev);
+  GNCA_LAUNCH_CHECK();
+  if (layout_out) *layout_out = d->kind == GNCA_DK_SALTPEPPER ? GNCA_DMG_PLANE_ALPHA : GNCA_DMG_PLANE;
+  return 0;
+}
+
+int gnca_apply_plane(int B, int C, int H, int W, float* state_dev, const float* plane_dev, int32_t layout, void* stream) {
+  if (!state_dev || !plane_dev || B <= 0 || C <= 0 || H <= 0 || W <= 0) return GNCA_ERR_ARG;
+  if (layout != GNCA_DMG_PLANE && layout != GNCA_DMG_PLANE_ALPHA) return GNCA_ERR_ARG;
+  if (layout == GNCA_DMG_PLANE_ALPHA && C < 4) return GNCA_ERR_ARG;
+  k_apply_plane<<<grid_for((size_t)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(B, C, H * W, state_dev, plane_dev,
+                                                                                 layout == GNCA_DMG_PLANE_ALPHA);
   GNCA_LAUNCH_CHECK();
   return 0;
 }

@@ -362,6 +362,20 @@ __device__ __forceinline__ void msg_project(const float (&xs)[C], float as, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// damage mask of a rollout (gnca_schedule.damage / damage_layout): dense [B][C][HW], or a per-cell plane [B][HW] applied
+// to every channel or to the alpha channel only
+// ------------------------------------------------------------------------------------------------
+struct DamageView {
+  const float* p;      // null: no damage
+  int layout;
+  __device__ __forceinline__ float at(int b, int ch, int cell, int C, int HW) const {
+    if (layout == GNCA_DMG_DENSE) return p[((size_t)b * C + ch) * HW + cell];
+    if (layout == GNCA_DMG_PLANE_ALPHA && ch != 3) return 1.f;
+    return p[(size_t)b * HW + cell];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

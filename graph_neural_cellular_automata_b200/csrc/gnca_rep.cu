@@ -53,7 +53,7 @@ struct RepArgs {
   uint32_t* masks;            // [T][B][3][kMaskWords] or null: sender-alive, active, post-alive bitmaps of every step
   float* u_over;              // [B*NC][over_cap][C] overflow of the in-smem u buffer
   int over_cap;
-  const float* damage;        // [B][C][HW] or null
+  DamageView damage;          // schedule.damage (dense or plane) or null
   int damage_step;
   unsigned long long* dbg;
   int dbg_cta;
@@ -390,8 +390,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
 
   for (int t = 0; t < R.T; ++t) {
     const int cur = t & 1;
-    if (R.damage && t == R.damage_step) {        // multiplicative damage on every replica (utils/damage.py masks)
-      const float* D = R.damage + sample_off;
+    if (R.damage.p && t == R.damage_step) {      // multiplicative damage on every replica (utils/damage.py masks)
       const int n8 = (HW + 7) & ~7;
 #pragma unroll 1
       for (int i = tid; i < n8 * C; i += kPT) {
@@ -399,7 +398,7 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
         const int cq = rest & 3, cgp = rest >> 2;
         const int cell = cgp * 8 + ci, ch = cq * 4 + c4;
         if (cell < HW) {
-          const float d = D[(size_t)ch * HW + cell];
+          const float d = R.damage.at(b, ch, cell, C, HW);
           if (ch == 3) sAg[cell] *= d; else sX[cell * C + ch] *= d;
         }
       }
@@ -636,12 +635,15 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     // Side jobs of the step, statically spread over warps 1..15 (warp 0 runs the GroupNorm exchange).  The BPTT history
     // of x_t must be stored BEFORE my partial goes out (that message tells the peers they may overwrite x_t here); the
     // fire bits of step t+1 touch no state, so a warp that had a tile generates them in the shadow of the exchange.
+    // the sparse-fire invariant (non-alive => alpha == 0) does not hold for the state a damage mask just produced: a cell
+    // kept alive by a neighbour the mask killed still carries its alpha and can cross the threshold by the idle drift
+    const bool dmg_now = R.damage.p && t == R.damage_step;
     auto side_jobs = [&](const bool fire, const bool hist) {
       const int nf = (t + 1 < R.T) ? n_fire_tasks : 0;
       float* hdst = R.hist ? R.hist + (size_t)t * a.B * C * HW + sample_off : nullptr;
       if (fire) {
 #pragma unroll 1
-        for (int task = kPW - 1 - warp; task < nf; task += kPW - 1) fire_task(task, t + 1, cur ^ 1, sparse_fire && t >= 1);
+        for (int task = kPW - 1 - warp; task < nf; task += kPW - 1) fire_task(task, t + 1, cur ^ 1, sparse_fire && t >= 1 && !dmg_now);
       }
       if (hist) {
 #pragma unroll 1
@@ -873,7 +875,7 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
   R.T = sched.T;
   R.x0 = x0; R.xT = xT; R.hist = hist; R.stats_hist = stats_hist; R.u_hist = u_hist;
   R.rec = rec; R.masks = masks;
-  R.damage = sched.damage; R.damage_step = sched.damage_step;
+  R.damage = DamageView{sched.damage, sched.damage_layout}; R.damage_step = sched.damage_step;
   R.KP = k > 8 ? 16 : 8;
   R.HWp = 4 * (((HW >> 2) + 31) & ~31) + 16;      // planes padded to whole warps of quads + one scratch quad
   R.inv_n = (float)(1.0 / ((double)C * (double)H * (double)W));

@@ -51,7 +51,7 @@ struct RepBwdArgs {
   float* GZ;                  // [B][HW][C] gz of the active cells of the current step, by slot (L2)
   float* RG;                  // [B][HW][64]   gy (48) | g_xs (16) of the active cells of the current step (L2)
   float* affpart;             // [B*NC][2C] dgamma | dbeta partials
-  const float* damage;
+  DamageView damage;
   int damage_step;
   unsigned long long* dbg;    // optional phase-cycle counters (GNCA_PHASE_TIMING=<cta>)
   int dbg_cta;
@@ -180,14 +180,13 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
   float dgam = 0.f, dbet = 0.f;              // this lane's channel c, summed over its cells / steps
 
   for (int t = R.T - 1; t >= 0; --t) {
-    const bool dmg = R.damage && t == R.damage_step;
+    const bool dmg = R.damage.p && t == R.damage_step;
     if (t >= my_steps) {                     // frozen: g passes through (the damage mask still multiplies x)
       if (dmg) {
-        const float* D = R.damage + sample_off;
 #pragma unroll 1
         for (int i = tid; i < nband * C; i += kQT) {
           const int cl = i / C, ch = i - cl * C;
-          sG[i] *= D[(size_t)ch * HW + band_lo + cl];
+          sG[i] *= R.damage.at(b, ch, band_lo + cl, C, HW);
         }
         __syncthreads();
       }
@@ -607,9 +606,8 @@ __global__ void __launch_bounds__(kQT, 1) k_rep_bwd(RepBwdArgs R, Packed P, cons
           }
         }
         if (dmg) {
-          const float* D = R.damage + sample_off + cell;
-          g.x *= D[(size_t)(4 * cq) * HW]; g.y *= D[(size_t)(4 * cq + 1) * HW];
-          g.z *= D[(size_t)(4 * cq + 2) * HW]; g.w *= D[(size_t)(4 * cq + 3) * HW];
+          g.x *= R.damage.at(b, 4 * cq, cell, C, HW); g.y *= R.damage.at(b, 4 * cq + 1, cell, C, HW);
+          g.z *= R.damage.at(b, 4 * cq + 2, cell, C, HW); g.w *= R.damage.at(b, 4 * cq + 3, cell, C, HW);
         }
         *reinterpret_cast<float4*>(sG + cl * C + 4 * cq) = g;
       }
@@ -921,7 +919,7 @@ int run_rep_bwd(const gnca_model& m, const Packed& P, const float* packed, int B
   R.inv_n = (float)(1.0 / ((double)C * (double)H * (double)W));
   R.rec = rec; R.hgh = hgh; R.masks = masks; R.stats = stats; R.gT = gT; R.g0 = g0; R.GZ = GZ; R.RG = RG;
   R.affpart = affpart;
-  R.damage = sched.damage; R.damage_step = sched.damage_step;
+  R.damage = DamageView{sched.damage, sched.damage_layout}; R.damage_step = sched.damage_step;
 
   int pick = -1, pick_gmax = 8;
   size_t pick_smem = 0;

@@ -39,7 +39,7 @@ struct ResidentArgs {
   float* hist;                // [T+1][B][C][HW] or null
   float* stats_hist;          // [T][B][2] or null
   float* u_hist;              // [T][B][C][HW] or null: masked pre-norm update of the active cells (for the backward)
-  const float* damage;        // [B][C][HW] or null
+  DamageView damage;          // schedule.damage (dense or plane) or null
   int damage_step;
   unsigned long long* dbg;    // optional phase-cycle counters (GNCA_PHASE_TIMING=<cta index>), else null
   int dbg_cta;
@@ -214,14 +214,13 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
   };
 
   for (int t = 0; t < R.T; ++t) {
-    if (R.damage && t == R.damage_step) {      // multiplicative damage on every copy we hold (own + halos)
-      const float* D = R.damage + sample_off;
+    if (R.damage.p && t == R.damage_step) {    // multiplicative damage on every copy we hold (own + halos)
 #pragma unroll 1
       for (int row = warp; row < C * RS; row += kRWarps) {
         const int c = row / RS, lr = row - c * RS;
-        const float* src = D + (size_t)c * HW + wrap_row(lr) * W;
+        const int cell0 = wrap_row(lr) * W;
 #pragma unroll 1
-        for (int x = lane; x < W; x += 32) sX[(size_t)c * PL + lr * W + x] *= src[x];
+        for (int x = lane; x < W; x += 32) sX[(size_t)c * PL + lr * W + x] *= R.damage.at(b, c, cell0 + x, C, HW);
       }
       __syncthreads();
     }
@@ -760,7 +759,7 @@ int run_resident_fwd(const gnca_model& m, const Packed& P, const float* packed, 
   R.fire_u_base = sched.fire_u;
   R.T = sched.T;
   R.x0 = x0; R.xT = xT; R.hist = hist; R.stats_hist = stats_hist; R.u_hist = u_hist;
-  R.damage = sched.damage; R.damage_step = sched.damage_step;
+  R.damage = DamageView{sched.damage, sched.damage_layout}; R.damage_step = sched.damage_step;
   const int radius = sched.max_offset;       // largest |dy| / |dx| in the schedule: sets the halo depth
   switch (m.C) {
     case 4: return launch_resident<4>(m, P, packed, R, B, radius, st);

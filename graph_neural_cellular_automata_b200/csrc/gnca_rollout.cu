@@ -9,8 +9,11 @@
 
 namespace gnca {
 
-__global__ void k_mul_inplace(size_t n, float* __restrict__ x, const float* __restrict__ m) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= m[i];
+__global__ void k_mul_inplace(size_t n, float* __restrict__ x, DamageView d, int C, int HW) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t bc = i / HW;
+    x[i] *= d.at((int)(bc / C), (int)(bc % C), (int)(i - bc * HW), C, HW);
+  }
 }
 
 struct RolloutWorkspace {
@@ -116,7 +119,7 @@ int gnca_rollout_fwd(const gnca_model* m, const float* packed_dev, int B, int H,
   GNCA_CHECK_CUDA(cudaMemcpyAsync(x_at(0), x0_dev, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
   for (int t = 0; t < T; ++t) {
     if (sched->damage && t == sched->damage_step) {
-      k_mul_inplace<<<(int)((N + 1023) / 1024 < 2368 ? (N + 1023) / 1024 : 2368), 256, 0, st>>>(N, x_at(t), sched->damage);
+      k_mul_inplace<<<(int)((N + 1023) / 1024 < 2368 ? (N + 1023) / 1024 : 2368), 256, 0, st>>>(N, x_at(t), DamageView{sched->damage, sched->damage_layout}, m->C, H * W);
       GNCA_LAUNCH_CHECK();
     }
     StepArgs a;
@@ -181,7 +184,7 @@ int gnca_rollout_bwd(const gnca_model* m, const float* packed_dev, int B, int H,
     rc = run_step_bwd(*m, P, packed_dev, a, stats_t, gcur, gnext, gparams_dev, fws, bws, t == T - 1, t == 0, st);
     if (rc) return rc;
     if (sched->damage && t == sched->damage_step) {
-      k_mul_inplace<<<(int)((N + 1023) / 1024 < 2368 ? (N + 1023) / 1024 : 2368), 256, 0, st>>>(N, gnext, sched->damage);
+      k_mul_inplace<<<(int)((N + 1023) / 1024 < 2368 ? (N + 1023) / 1024 : 2368), 256, 0, st>>>(N, gnext, DamageView{sched->damage, sched->damage_layout}, m->C, H * W);
       GNCA_LAUNCH_CHECK();
     }
     gcur = gnext;

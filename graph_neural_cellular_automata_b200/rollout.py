@@ -35,8 +35,9 @@ class Schedule:
     fire_u: Optional[torch.Tensor] = None   # [T,B,H,W] f32 (row b = sample b)
     philox_seed: int = 0
     philox_offset: int = 0
-    damage: Optional[torch.Tensor] = None   # [B,C,H,W] multiplicative mask
+    damage: Optional[torch.Tensor] = None   # multiplicative mask: [B,C,H,W] (layout 0) or a per-cell plane [B,H,W]
     damage_step: int = 0
+    damage_layout: int = 0                  # 0 dense, 1 plane on every channel, 2 plane on alpha only (include/gnca.h)
     total_updates: Optional[int] = None     # sum_b steps_b (host int, for throughput accounting)
     max_offset: int = 0                     # max(|dy|,|dx|) over the offsets (halo depth of the resident kernel)
 
@@ -44,7 +45,7 @@ class Schedule:
         p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
         return GncaSchedule(self.T, self.k, p(self.fire_rate), p(self.message_gain), p(self.offsets), p(self.steps),
                             p(self.fire_u), C.c_uint64(self.philox_seed), C.c_uint64(self.philox_offset),
-                            p(self.damage), self.damage_step, self.max_offset)
+                            p(self.damage), self.damage_step, self.max_offset, int(self.damage_layout), 0)
 
 
 class _PinnedRing:
@@ -115,6 +116,8 @@ def make_schedule(model, B: int, H: int, W: int, T: int, *, fire_rate: Union[flo
     * fire="torch": one `torch.rand(B,1,H,W)` per step on the model device (bit-identical stream to T forward
       calls with a fixed fire_rate < 1); fire="philox": in-kernel Philox4x32-10 keyed by `seed` (no HBM traffic,
       statistically equivalent, different numbers); or pass recorded `fire_u` [T,B,H,W].
+    * damage: a `utils.damage.Damage` (descriptor evaluated to a per-cell plane, applied in-kernel before step
+      `damage_step`) or a dense [B,C,H,W] mask tensor.
     * message_gains: per-step `model.message_gain` (the trainer sets gain or 0 per step, train...:312-319);
       default = model.message_gain on steps with t % message_every == 0, else 0.
     """
@@ -148,8 +151,16 @@ def make_schedule(model, B: int, H: int, W: int, T: int, *, fire_rate: Union[flo
     else:
         total = B * T
     dev = _upload(arrs, device)
+    damage_layout = 0
+    if damage is not None and hasattr(damage, "plane"):              # utils.damage.Damage
+        damage_layout, damage = int(damage.layout), GF._require_cuda_f32(damage.plane, "damage plane")
+        if tuple(damage.shape) != (B, H, W):
+            raise ValueError(f"damage plane has shape {tuple(damage.shape)}, expected {(B, H, W)}")
+    elif damage is not None:
+        damage = GF._require_cuda_f32(damage, "damage")
     sched = Schedule(T=T, k=k, fire_rate=dev[0], message_gain=dev[1], offsets=dev[2] if off.size else None,
                      steps=dev[3] if steps is not None else None, damage=damage, damage_step=int(damage_step),
+                     damage_layout=damage_layout,
                      total_updates=total, max_offset=int(np.abs(off).max()) if off.size else 0)
     needs_fire = bool((fr < 1.0).any())
     if fire_u is not None:

@@ -20,10 +20,24 @@ class SamplePool:
     def __len__(self) -> int:
         return self.pool.shape[0]
 
+    def _index(self, idx: Sequence[int]) -> torch.Tensor:
+        """Slot indices on the pool's device.  On CUDA the list goes through pinned memory with a non-blocking copy: a
+        pageable `torch.as_tensor(list, device=cuda)` would make the host wait for everything queued on the stream (one
+        hidden synchronisation per training step)."""
+        if self.pool.is_cuda:
+            host = torch.tensor(list(idx), dtype=torch.int64).pin_memory()
+            dev = host.to(self.pool.device, non_blocking=True)
+            self._keep = (host, dev)             # the pinned source stays alive until the next call has queued its own copy
+            return dev
+        return torch.as_tensor(list(idx), device=self.pool.device)
+
     def sample(self, batch_size) -> Tuple[List[int], torch.Tensor]:
         idx = random.sample(range(len(self)), batch_size)
-        batch = self.pool[torch.as_tensor(idx, device=self.pool.device)]     # gather = fresh copy
+        self._last = (idx, self._index(idx))
+        batch = self.pool[self._last[1]]                                     # gather = fresh copy
         return idx, batch
 
     def replace(self, idx: Sequence[int], new_samples: torch.Tensor) -> None:
-        self.pool[torch.as_tensor(list(idx), device=self.pool.device)] = new_samples.detach()
+        last = getattr(self, "_last", None)
+        dev_idx = last[1] if last is not None and last[0] is idx else self._index(idx)
+        self.pool[dev_idx] = new_samples.detach()

@@ -107,43 +107,59 @@ class GraphNCATrainer:
 
     def _draw_schedule(self, epoch: int, B: int, state: torch.Tensor):
         """Appendix B, rows 5 ... end of rollout: regime, step counts, then per step (fire rate, gating, offsets,
-        fire uniforms)."""
+        fire uniforms).
+
+        fire="torch" replays the reference's draws call for call (device `torch.randint` step counts -> the iteration's ONE
+        host sync, one 1-element `uniform_` per step, one `torch.rand` per step, one `random.sample` per step).
+        fire="philox" is the production mode: same distributions, but nothing waits for the device -- step counts come
+        from the host generator, the T fire rates from one device call, the T offset draws from one block replay of the
+        python RNG stream, fire masks from the in-kernel Philox stream; the whole iteration is enqueued asynchronously."""
         cfg, dev = self.cfg, self.device
+        fast = cfg.fire == "philox"
         if random.random() < cfg.long_rollout_prob:
             lo, hi = cfg.long_rollout_steps_min, cfg.long_rollout_steps_max
         else:
             lo, hi = cfg.nca_steps_min, cfg.nca_steps_max
-        nca_steps = torch.randint(lo, hi + 1, (B,), device=dev)
-        steps_host = nca_steps.cpu().numpy()                              # the iteration's one host sync
+        if fast:
+            steps_host = torch.randint(lo, hi + 1, (B,)).numpy()              # host generator: no device round trip
+        else:
+            steps_host = torch.randint(lo, hi + 1, (B,), device=dev).cpu().numpy()   # train...:297-301; the one host sync
         T = int(steps_host.max())
         base_gain = scheduled_message_gain(epoch, cfg.message_gain)
         H = W = self.img
         fr_dev = torch.empty(T, dtype=torch.float32, device=dev)
         gains, offsets = [], []
-        fire_u = torch.empty(T, B, 1, H, W, dtype=torch.float32, device=dev) if cfg.fire == "torch" else None
-        for t in range(T):
-            fr_dev[t:t + 1].uniform_(cfg.fire_rate_min, cfg.fire_rate_max)           # train...:310
-            use_graph = True
-            if cfg.message_every > 1:
-                use_graph = (t % cfg.message_every == 0)
-            elif cfg.message_rate < 1.0:
-                use_graph = random.random() < cfg.message_rate
-            gains.append(base_gain if use_graph else 0.0)
-            if self.is_graph:
-                offsets.append(self.model.graph.draw_offsets())                       # graph_augmentation.py:121
-            if fire_u is not None:
-                act = np.nonzero(steps_host > t)[0]
-                if len(act) == B:
-                    torch.rand(B, 1, H, W, out=fire_u[t])                             # ncagraph.py:145
-                else:
-                    fire_u[t, torch.as_tensor(act, device=dev)] = torch.rand(len(act), 1, H, W, device=dev)
+        fire_u = torch.empty(T, B, 1, H, W, dtype=torch.float32, device=dev) if not fast else None
+        interleaved = cfg.message_every <= 1 and cfg.message_rate < 1.0       # random.random() between the offset draws
+        if fast:
+            fr_dev.uniform_(cfg.fire_rate_min, cfg.fire_rate_max)
+        if fast and not interleaved:
+            gains = [base_gain if (cfg.message_every <= 1 or t % cfg.message_every == 0) else 0.0 for t in range(T)]
+            offsets = self.model.graph.draw_offsets_array(T) if self.is_graph else None
+        else:
+            for t in range(T):
+                if not fast:
+                    fr_dev[t:t + 1].uniform_(cfg.fire_rate_min, cfg.fire_rate_max)       # train...:310
+                use_graph = True
+                if cfg.message_every > 1:
+                    use_graph = (t % cfg.message_every == 0)
+                elif cfg.message_rate < 1.0:
+                    use_graph = random.random() < cfg.message_rate
+                gains.append(base_gain if use_graph else 0.0)
+                if self.is_graph:
+                    offsets.append(self.model.graph.draw_offsets())                   # graph_augmentation.py:121
+                if fire_u is not None:
+                    act = np.nonzero(steps_host > t)[0]
+                    if len(act) == B:
+                        torch.rand(B, 1, H, W, out=fire_u[t])                         # ncagraph.py:145
+                    else:
+                        fire_u[t, torch.as_tensor(act, device=dev)] = torch.rand(len(act), 1, H, W, device=dev)
         sh = self.shard
         sched = make_schedule(self.model, sh.local_batch, H, W, T, fire_rate=[0.0] * T, message_gains=gains,
                               offsets=offsets if self.is_graph else None, steps=steps_host[sh.lo:sh.hi].tolist(),
-                              fire="philox", seed=random.getrandbits(63) if cfg.fire == "philox" else 0,
-                              device=dev)
+                              fire="philox", seed=random.getrandbits(63) if fast else 0, device=dev)
         sched.fire_rate = fr_dev                                            # device-resident draws, no .item()
-        if cfg.fire == "philox" and sh.world > 1:
+        if fast and sh.world > 1:
             # the in-kernel counter is indexed by the LOCAL sample (t*B_local + b): give every rank its own block range so
             # that the fire masks of the global batch are independent, like the reference's one torch.rand over the batch
             sched.philox_offset = sh.rank * ((T * sh.local_batch * H * W + 3) // 4)
@@ -156,11 +172,11 @@ class GraphNCATrainer:
         Bg = cfg.batch_size
         idx, batch = self.pool.sample(Bg)                                   # pool.py:28 (global batch everywhere)
         state = batch
-        D = sample_damage_mask(state, cfg.damage, epoch) if cfg.damage else None   # damage.py:101-138
+        D = sample_damage_mask(state, cfg.damage, epoch, fast=cfg.fire == "philox") if cfg.damage else None   # damage.py:101-138
         sched, steps_host = self._draw_schedule(epoch, Bg, state)
         if D is not None:                       # applied in-kernel to x_0 (the reference damages before the rollout)
-            sched.damage = sh.take(D.expand_as(state)).contiguous()
-            sched.damage_step = 0
+            mine = D.take(sh.lo, sh.hi)         # descriptor evaluated to a per-cell plane [B,H,W]: no [B,C,H,W] mask
+            sched.damage, sched.damage_layout, sched.damage_step = mine.plane, mine.layout, 0
         x0 = sh.take(state).contiguous()
         desc, packed = self.model.model_desc(), self.model.packed_weights()
         impl = {"auto": 0, "streaming": 1, "resident": 2, "banded": 3}[cfg.rollout_impl]
@@ -172,7 +188,11 @@ class GraphNCATrainer:
         per_global = sh.allgather(per_local)
         worst = worst_k_indices(per_global, cfg.reset_worst_prob)            # train...:378-380 (bit-exact indices)
         do_reseed = random.random() < cfg.random_reseed_prob
-        rand_idx = int(torch.randint(0, Bg, (1,), device=self.device).item()) if do_reseed else None
+        if do_reseed:      # train...:386-389; fast mode draws the slot on the host (no device round trip)
+            rand_idx = int(torch.randint(0, Bg, (1,)).item()) if cfg.fire == "philox" else \
+                int(torch.randint(0, Bg, (1,), device=self.device).item())
+        else:
+            rand_idx = None
         new_states = sh.allgather(xT)
         if worst is not None and worst.numel() > 0:
             new_states = new_states.clone()

@@ -84,10 +84,45 @@ typedef struct gnca_schedule {
   const float* fire_u;        /* [T][B][H][W] uniforms (the reference's torch.rand draws) or NULL */
   uint64_t philox_seed;       /* used when fire_u == NULL: in-kernel Philox4x32-10 uniforms */
   uint64_t philox_offset;
-  const float* damage;        /* [B][C][H][W] multiplicative mask applied to x BEFORE step damage_step, or NULL */
+  const float* damage;        /* multiplicative mask applied to x BEFORE step damage_step, or NULL; layout below */
   int32_t damage_step;
   int32_t max_offset;         /* max(|dy|,|dx|) over all offsets (halo depth of the resident kernel); 0 = unknown */
+  int32_t damage_layout;      /* GNCA_DMG_DENSE [B][C][H][W] | GNCA_DMG_PLANE [B][H][W] on every channel |
+                                 GNCA_DMG_PLANE_ALPHA [B][H][W] on the alpha channel only (salt & pepper) */
+  int32_t reserved_;
 } gnca_schedule;
+
+#define GNCA_DMG_DENSE 0
+#define GNCA_DMG_PLANE 1
+#define GNCA_DMG_PLANE_ALPHA 2
+
+/* Damage DESCRIPTOR (src/utils/damage.py:16-98, policy :101-138): one kind + one size for the whole batch, per-sample
+ * geometry.  gnca_damage_plane evaluates it in closed form into a per-cell plane [B][H][W] (square / circle / stripes /
+ * gaussian from the positions; alpha_drop / saltpepper from the caller's uniforms), which the rollout kernels multiply
+ * in at `damage_step` (schedule.damage with layout GNCA_DMG_PLANE / GNCA_DMG_PLANE_ALPHA) -- no [B][C][H][W] mask. */
+#define GNCA_DK_SQUARE 1      /* cutout_square_  :16-24   pos[b] = top-left (y, x), side `size`                         */
+#define GNCA_DK_CIRCLE 2      /* cutout_circle_  :27-37   pos[b] = centre, radius `size`                                */
+#define GNCA_DK_STRIPE_H 3    /* stripe_wipe_    :40-51   rows  [pos[0][0], +size) of EVERY sample                      */
+#define GNCA_DK_STRIPE_V 4    /*                           cols  [pos[0][0], +size)                                      */
+#define GNCA_DK_GAUSSIAN 5    /* gaussian_hole_  :87-98   clamp(1 - exp(-r2 / (2 (size*softness)^2)), 0, 1)             */
+#define GNCA_DK_ALPHA_DROP 6  /* alpha_dropout_  :54-66   0 where rand < p and alpha > alpha_thr (hard: all channels)   */
+#define GNCA_DK_SALTPEPPER 7  /* salt_pepper_alpha_ :69-73  0 where rand < p, alpha channel only                        */
+typedef struct gnca_damage {
+  int32_t kind;
+  int32_t size;
+  float softness;             /* gaussian */
+  float p;                    /* alpha_drop / saltpepper */
+  float alpha_thr;            /* alpha_drop */
+  int32_t reserved_;
+  const int64_t* pos;         /* device [B][2] (y, x) -- what torch.randint drew, never read back by the host */
+  const float* rand;          /* device [B][H][W] uniforms (torch.rand_like(alpha)) for kinds 6, 7 */
+} gnca_damage;
+/* plane[b][y][x] of the descriptor; `state` ([B][C][H][W]) is read for alpha_drop only.  *layout_out = the schedule
+ * layout the plane must be applied with. */
+int gnca_damage_plane(const gnca_damage* d, int B, int C, int H, int W, const float* state_dev, float* plane_dev,
+                      int32_t* layout_out, void* stream);
+/* state *= plane (layout GNCA_DMG_PLANE or GNCA_DMG_PLANE_ALPHA), in place */
+int gnca_apply_plane(int B, int C, int H, int W, float* state_dev, const float* plane_dev, int32_t layout, void* stream);
 
 int gnca_version(void);
 const char* gnca_error_string(int code);

@@ -71,4 +71,5 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_lib.GncaModel) == 32
     assert C.sizeof(_lib.GncaLayout) == 14 * 8
     # gnca_schedule: 2 int32, 5 pointers, 2 uint64, 1 pointer, 2 int32
-    assert C.sizeof(_lib.GncaSchedule) == 8 + 5 * 8 + 16 + 8 + 8
+    assert C.sizeof(_lib.GncaSchedule) == 8 + 5 * 8 + 16 + 8 + 8 + 8
+    assert C.sizeof(_lib.GncaDamage) == 24 + 16

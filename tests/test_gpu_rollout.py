@@ -182,3 +182,46 @@ def test_damage_in_rollout():
                 x = x * D
             x = m.step(x, 0.5, fire_u=fu[t].unsqueeze(1), chosen=offs[t])
     assert torch.equal(xT, x)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("kind", ["square", "circle", "stripes", "gaussian", "alpha_drop", "saltpepper"])
+def test_damage_descriptor_in_rollout(impl, kind):
+    """A damage DESCRIPTOR (utils/damage.py `Damage`: per-cell plane, all channels or alpha only) applied in-kernel at
+    step td == rollout to td, multiply by the dense mask, continue; and forward + all gradients are bit-identical to the
+    same rollout fed the equivalent dense [B,C,H,W] mask (checks the plane indexing of every kernel, backward included)."""
+    from graph_neural_cellular_automata_b200.utils import damage as DM
+    m = graph_model(True)
+    g = load_golden("graph_torus_step.npz")
+    x0 = T32(g["x_in"]).to(DEV)
+    T, td = 6, 3
+    torch.manual_seed(4); random.seed(4)
+    Dm = {"square": lambda: DM.square_mask(x0, 9), "circle": lambda: DM.circle_mask(x0, 6),
+          "stripes": lambda: DM.stripe_mask(x0, 5, "auto"), "gaussian": lambda: DM.gaussian_mask(x0, 6, 0.35),
+          "alpha_drop": lambda: DM.alpha_dropout_mask(x0, 0.3, 0.12, True), "saltpepper": lambda: DM.salt_pepper_mask(x0, 0.2)}[kind]()
+    dense = Dm.dense(x0)
+    assert Dm.layout == (2 if kind == "saltpepper" else 1) and float((dense != 1).sum()) > 0
+    if kind == "saltpepper":
+        assert bool((dense[:, :3] == 1).all()) and bool((dense[:, 4:] == 1).all())
+    offs = [m.graph.draw_offsets() for _ in range(T)]
+    fu = torch.rand(T, 2, 40, 40, device=DEV)
+
+    def run(dmg):
+        for p_ in m.parameters():
+            p_.grad = None
+        sched = make_schedule(m, 2, 40, 40, T, fire_rate=0.5, offsets=offs, fire_u=fu, damage=dmg, damage_step=td)
+        xg = x0.clone().requires_grad_(True)
+        xT = _supported(impl, lambda: rollout(m, xg, sched, impl=impl))
+        xT[:, :4].square().mean().backward()
+        return xT.detach(), xg.grad.clone(), {n: p_.grad.clone() for n, p_ in m.named_parameters() if p_.grad is not None}
+
+    a, ga, pa = run(Dm)
+    b, gb, pb = run(dense)
+    assert torch.equal(a, b) and torch.equal(ga, gb)
+    assert all(torch.equal(pa[n], pb[n]) for n in pa)
+    with torch.no_grad():
+        s1 = make_schedule(m, 2, 40, 40, td, fire_rate=0.5, offsets=offs[:td], fire_u=fu[:td].contiguous())
+        s2 = make_schedule(m, 2, 40, 40, T - td, fire_rate=0.5, offsets=offs[td:], fire_u=fu[td:].contiguous())
+        mid = rollout(m, x0, s1, impl="streaming")
+        two = rollout(m, (mid * dense).contiguous(), s2, impl="streaming")
+    assert rel_err(a.cpu(), two.cpu()) < 1e-6
