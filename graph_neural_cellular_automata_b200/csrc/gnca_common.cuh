@@ -140,6 +140,7 @@ struct StepArgs {
   double* partials;                   // [B][nchunks][2]
   int nchunks, chunk;                 // k_update work split: cells per block and blocks per sample
   int npart;                          // GroupNorm partial slots per sample in `partials` (nchunks, or 3*nchunks: k_update_tc)
+  const float* stats_ready;           // [B][2] (mean, rstd) already finished by the update path (k_update_tc2) or null
   Offsets off;                        // host-supplied offsets (single step)
 };
 

@@ -10,6 +10,7 @@ struct FwdWorkspace {
   float* rowsum;      // [B][C][H]
   float* attn_w;      // [B][MAX_K]
   float* absmean;     // [B][H][W]
+  void* tc2;          // tile masks / lists / partials of k_update_tc2 (update_tc2_workspace_bytes)
   size_t bytes;
 };
 
@@ -54,6 +55,12 @@ constexpr int kTcChunk = 1024;
 bool update_tc_supported(const gnca_model& m, const StepArgs& a);
 int launch_update_tc(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, const uint16_t* glist,
                      const int* prefix, cudaStream_t st);
+
+// dense-tile, TMA-staged tensor-core k_update (gnca_update_tc2.cu): H % 8 == 0, W % 16 == 0.  Finishes the GroupNorm
+// statistics itself: a.stats_ready points at (mean, rstd) per sample afterwards (written to a.stats when that is set).
+size_t update_tc2_workspace_bytes(int B, int H, int W);
+bool update_tc2_supported(const gnca_model& m, const StepArgs& a);
+int launch_update_tc2(const gnca_model& m, const Packed& P, const float* packed, StepArgs& a, void* ws, cudaStream_t st);
 
 // cluster-resident forward rollout (gnca_resident.cu); GNCA_ERR_UNSUPPORTED when the configuration has no
 // resident kernel (zero-padded graph shift, sample too large for the cluster's shared memory)

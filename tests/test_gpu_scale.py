@@ -42,7 +42,15 @@ def _blobs(B):
     return x
 
 
-def test_one_step_vs_oracle_at_scale():
+@pytest.mark.parametrize("kernel", ["tc", "tc2_tma", "ffma"])
+def test_one_step_vs_oracle_at_scale(kernel, monkeypatch):
+    """All three k_update variants of the large-problem path: compacted tensor-core tiles (default), dense TMA-staged
+    tensor-core tiles (GNCA_TC_V2=1), the round-1 FFMA kernel (GNCA_NO_TC=1)."""
+    monkeypatch.delenv("GNCA_TC_V2", raising=False); monkeypatch.delenv("GNCA_NO_TC", raising=False)
+    if kernel == "tc2_tma":
+        monkeypatch.setenv("GNCA_TC_V2", "1")
+    elif kernel == "ffma":
+        monkeypatch.setenv("GNCA_NO_TC", "1")
     m, p = _model()
     B = 5                                            # 5 * 64 chunks >= 2 * 148 blocks: the balanced large-problem path
     x = _blobs(B)
