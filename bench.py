@@ -466,15 +466,20 @@ def run_trainer(args, world, rank, local_rank, dev, steps, warmup, regime="short
         dmg = {"start_epoch": 100, "prob": 1.0, "kinds": {"square": 0.35, "circle": 0.25, "stripes": 0.1, "alpha_drop": 0.15,
                "saltpepper": 0.05, "gaussian": 0.1}, "size_min": 6, "size_max": 18, "stripe_width": 6, "alpha_thr": 0.2,
                "alpha_dropout_p": 0.15, "salt_pepper_p": 0.02, "gaussian_softness": 0.35}
+    # N > 1: the pool is partitioned over the ranks (rank r owns 1024 / N slots and draws its share of the batch from them:
+    # no state all-gather; --pool replicated keeps the reference's global draw + all-gather for comparison)
+    sharding = "owner" if (world > 1 and args.pool == "owner") else "replicated"
     tcfg = TrainConfig(batch_size=Bg, pool_size=1024, long_rollout_prob=1.0 if regime == "long" else 0.0, fire="philox",
-                       rollout_impl=args.rollout_impl, damage=dmg)
+                       rollout_impl=args.rollout_impl, damage=dmg, pool_sharding=sharding)
     tr = GraphNCATrainer(model, target, tcfg)
     # pool of mixed ages: every slot rolled 0..160 steps from its seed, no grad
+    n_slots = tr.pool.pool.shape[0]
+    chunk = min(256, n_slots)
     with torch.no_grad():
-        for i0 in range(0, 1024, 256):
-            ages = [random.randint(0, 160) for _ in range(256)]
-            sched = make_schedule(model, 256, 40, 40, max(ages), fire_rate=0.6, steps=ages, fire="philox", seed=77 + i0)
-            tr.pool.pool[i0:i0 + 256] = rollout(model, tr.pool.pool[i0:i0 + 256].contiguous(), sched)
+        for i0 in range(0, n_slots, chunk):
+            ages = [random.randint(0, 160) for _ in range(chunk)]
+            sched = make_schedule(model, chunk, 40, 40, max(ages), fire_rate=0.6, steps=ages, fire="philox", seed=77 + i0 + 1000 * rank)
+            tr.pool.pool[i0:i0 + chunk] = rollout(model, tr.pool.pool[i0:i0 + chunk].contiguous(), sched)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     for _ in range(warmup):
         tr.train_step(epoch=300)
@@ -549,7 +554,9 @@ def run_trainer(args, world, rank, local_rank, dev, steps, warmup, regime="short
                                                                                            ", damage policy on every step" if damage else ""),
                        "global_batch": Bg, "B_per_gpu": Bg // world, "pool": 1024, "steps": "randint(48,80)" if regime == "short" else "randint(200,400)",
                        "fire_rate": "U(0.5,0.9) per step", "message_every": 3, "fire_rng": "in-kernel philox (per-rank stream offset)",
-                       "parallelism": f"dp{world}: batch sharded, NCCL all-reduce of the 9,169-float gradient + all-gather of losses / final states"},
+                       "pool_sharding": sharding,
+                       "parallelism": f"dp{world}: batch sharded, NCCL all-reduce of the 9,169-float gradient + all-gather of the per-sample losses"
+                                      + ("" if sharding == "owner" or world == 1 else " and of the final states (replicated pool)")},
             "roofline": roof}
 
 
@@ -562,6 +569,8 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--rollout-impl", default="auto", choices=["auto", "streaming", "resident", "banded"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pool", default="owner", choices=["owner", "replicated"],
+                    help="N > 1 training: pool partitioned over the ranks (default) or replicated with a state all-gather")
     ap.add_argument("--no-train-extra", action="store_true", help="skip the fwd+bwd (c3) measurement of the default run")
     ap.add_argument("--T", type=int, default=0, help="development: override the number of CA steps per rollout")
     ap.add_argument("--B", type=int, default=0, help="development: override the per-GPU batch")

@@ -50,6 +50,11 @@ class TrainConfig:
     damage: Dict = field(default_factory=dict)
     fire: str = "torch"            # "torch": the reference's torch.rand stream; "philox": in-kernel RNG (fast)
     rollout_impl: str = "auto"
+    # data-parallel pool: "replicated" = every rank holds the whole pool and draws the reference's global batch
+    # (random.sample over all slots; needs an all-gather of the final states every step), "owner" = rank r owns
+    # pool_size / world slots and draws its share of the batch from them (no state traffic at all; the batch is
+    # then stratified over the ranks -- same marginal law per slot, not the reference's joint law)
+    pool_sharding: str = "replicated"
 
     @staticmethod
     def from_reference_config(cfg: dict) -> "TrainConfig":
@@ -96,7 +101,13 @@ class GraphNCATrainer:
         self.n_ch, self.img = model.n_channels, model.img_size
         self.seed_fn = seed_fn or (lambda batch_size=1: trainer_seed(self.n_ch, self.img, batch_size, self.device))
         self.shard = Shard(cfg.batch_size)
-        self.pool = SamplePool(cfg.pool_size, self.seed_fn, device=self.device)
+        self.owner_pool = cfg.pool_sharding == "owner" and self.shard.world > 1
+        if cfg.pool_sharding not in ("replicated", "owner"):
+            raise ValueError("pool_sharding must be 'replicated' or 'owner'")
+        if self.owner_pool and cfg.pool_size % self.shard.world:
+            raise ValueError("pool_size must be divisible by the world size for pool_sharding='owner'")
+        self.pool = SamplePool(cfg.pool_size // self.shard.world if self.owner_pool else cfg.pool_size, self.seed_fn,
+                               device=self.device)
         self.opt = FusedNormalizedAdam(model, lr=cfg.learning_rate, weight_decay=cfg.weight_decay, normalize=True)
         self.is_graph = bool(getattr(model, "_is_graph", False))
         self.last: Dict = {}
@@ -170,14 +181,22 @@ class GraphNCATrainer:
     def train_step(self, epoch: int = 1) -> Dict:
         cfg, sh = self.cfg, self.shard
         Bg = cfg.batch_size
-        idx, batch = self.pool.sample(Bg)                                   # pool.py:28 (global batch everywhere)
-        state = batch
-        D = sample_damage_mask(state, cfg.damage, epoch, fast=cfg.fire == "philox") if cfg.damage else None   # damage.py:101-138
+        fast = cfg.fire == "philox"
+        if self.owner_pool:     # my share of the batch from my own slots (same host-RNG consumption on every rank)
+            idx, state = self.pool.sample(sh.local_batch)
+            x0 = state.contiguous()
+        else:
+            idx, state = self.pool.sample(Bg)                               # pool.py:28 (global batch everywhere)
+            x0 = None
+        # damage.py:101-138 -- the policy draws (gate, kind, size) are batch-level and identical on every rank; with an
+        # owner-sharded pool the geometry is drawn for the local samples only
+        D = sample_damage_mask(state, cfg.damage, epoch, fast=fast) if cfg.damage else None
         sched, steps_host = self._draw_schedule(epoch, Bg, state)
         if D is not None:                       # applied in-kernel to x_0 (the reference damages before the rollout)
-            mine = D.take(sh.lo, sh.hi)         # descriptor evaluated to a per-cell plane [B,H,W]: no [B,C,H,W] mask
+            mine = D if self.owner_pool else D.take(sh.lo, sh.hi)           # per-cell plane [B,H,W]: no [B,C,H,W] mask
             sched.damage, sched.damage_layout, sched.damage_step = mine.plane, mine.layout, 0
-        x0 = sh.take(state).contiguous()
+        if x0 is None:
+            x0 = sh.take(state).contiguous()
         desc, packed = self.model.model_desc(), self.model.packed_weights()
         impl = {"auto": 0, "streaming": 1, "resident": 2, "banded": 3}[cfg.rollout_impl]
         xT, hist = rollout_fwd_raw(desc, packed, x0, sched, history=True, impl=impl, keep_x=False)
@@ -185,21 +204,35 @@ class GraphNCATrainer:
         _, gflat = rollout_bwd_raw(desc, packed, hist, sched, gxT, impl=impl)
         sh.allreduce_sum_(gflat)                                             # the one data-path collective
         self.opt.step(gflat, lr=self.lr_at(epoch))                           # normalise AFTER the all-reduce
-        per_global = sh.allgather(per_local)
-        worst = worst_k_indices(per_global, cfg.reset_worst_prob)            # train...:378-380 (bit-exact indices)
+        per_global = sh.allgather(per_local)                                 # B floats: global worst-k stays bit-exact
+        worst = worst_k_indices(per_global, cfg.reset_worst_prob)            # train...:378-380
         do_reseed = random.random() < cfg.random_reseed_prob
         if do_reseed:      # train...:386-389; fast mode draws the slot on the host (no device round trip)
-            rand_idx = int(torch.randint(0, Bg, (1,)).item()) if cfg.fire == "philox" else \
+            rand_idx = int(torch.randint(0, Bg, (1,)).item()) if fast else \
                 int(torch.randint(0, Bg, (1,), device=self.device).item())
         else:
             rand_idx = None
-        new_states = sh.allgather(xT)
-        if worst is not None and worst.numel() > 0:
-            new_states = new_states.clone()
-            new_states[worst] = self.seed_fn(len(worst))
-        if do_reseed:
-            new_states = new_states.clone()
-            new_states[rand_idx:rand_idx + 1] = self.seed_fn(1)
+        if self.owner_pool:
+            # every rank reseeds and stores only ITS samples: no state leaves the GPU.  Membership of the global worst-k /
+            # reseed slot in my shard is decided on the device (mask), so the step stays free of host syncs.
+            new_states = xT
+            n_w = 0 if worst is None else int(worst.numel())
+            if n_w > 0 or do_reseed:
+                hit = torch.zeros(Bg, dtype=torch.bool, device=self.device)
+                if n_w > 0:
+                    hit[worst] = True
+                if do_reseed:
+                    hit[rand_idx] = True
+                mine = hit[sh.lo:sh.hi].view(-1, 1, 1, 1)
+                new_states = torch.where(mine, self.seed_fn(sh.local_batch), xT)
+        else:
+            new_states = sh.allgather(xT)
+            if worst is not None and worst.numel() > 0:
+                new_states = new_states.clone()
+                new_states[worst] = self.seed_fn(len(worst))
+            if do_reseed:
+                new_states = new_states.clone()
+                new_states[rand_idx:rand_idx + 1] = self.seed_fn(1)
         self.pool.replace(idx, new_states)
         self.last = {"per_sample": per_global, "loss": per_global.mean(), "steps": steps_host, "worst": worst,
                      "gflat": gflat, "cell_updates": int(np.minimum(steps_host, sched.T).sum()) * self.img * self.img}

@@ -26,7 +26,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _run(rank, world, port, out):
+def _run(rank, world, port, out, sharding="replicated"):
     if world > 1:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -40,14 +40,14 @@ def _run(rank, world, port, out):
     m = m.cuda()
     target = torch.from_numpy(np.load(os.path.join(GOLDEN, "target_gecko_surrogate.npy"))).cuda()
     cfg = TrainConfig(batch_size=8, pool_size=32, nca_steps_min=10, nca_steps_max=16, long_rollout_prob=0.0, fire="torch",
-                      reset_worst_prob=0.25, random_reseed_prob=1.0, damage=DMG)
+                      reset_worst_prob=0.25, random_reseed_prob=1.0, damage=DMG, pool_sharding=sharding)
     tr = GraphNCATrainer(m, target, cfg)
     rec = []
     for it in range(2):
         o = tr.train_step(epoch=150)
         rec.append({"per": o["per_sample"].cpu(), "worst": o["worst"].cpu(), "gflat": o["gflat"].cpu(), "steps": o["steps"].copy()})
     torch.cuda.synchronize()
-    out[(world, rank)] = {"rec": rec, "flat": tr.opt.flat.cpu(), "pool": tr.pool.pool.cpu()}
+    out[(world, rank, sharding)] = {"rec": rec, "flat": tr.opt.flat.cpu(), "pool": tr.pool.pool.cpu()}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -58,7 +58,7 @@ def test_two_ranks_equal_one_rank():
     out = mgr.dict()
     mp.spawn(_run, args=(1, 0, out), nprocs=1, join=True)
     mp.spawn(_run, args=(2, _free_port(), out), nprocs=2, join=True)
-    one, r0, r1 = out[(1, 0)], out[(2, 0)], out[(2, 1)]
+    one, r0, r1 = out[(1, 0, "replicated")], out[(2, 0, "replicated")], out[(2, 1, "replicated")]
     for it in range(2):
         a, b, c = one["rec"][it], r0["rec"][it], r1["rec"][it]
         assert np.array_equal(a["steps"], b["steps"]) and np.array_equal(a["steps"], c["steps"])     # same host RNG replay
@@ -69,3 +69,24 @@ def test_two_ranks_equal_one_rank():
     assert torch.equal(r0["flat"], r1["flat"]) and rel_err(r0["flat"], one["flat"]) < 1e-6           # parameters after 2 Adam steps
     assert torch.equal(r0["pool"], r1["pool"])                                                       # replicated pool stays replicated
     assert rel_err(r0["pool"], one["pool"]) < 1e-5
+
+
+def test_owner_sharded_pool_two_ranks():
+    """pool_sharding="owner" (rank r owns pool_size / world slots, no state all-gather): both ranks agree on the
+    all-reduced gradient, the global per-sample losses, the worst-k indices and the parameters; each rank's pool shard has
+    pool_size / world slots, changed only in the slots it drew, with its members of the global worst-k set reseeded."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_run, args=(2, _free_port(), out, "owner"), nprocs=2, join=True)
+    r0, r1 = out[(2, 0, "owner")], out[(2, 1, "owner")]
+    assert r0["pool"].shape[0] == 16 and r1["pool"].shape[0] == 16
+    for it in range(2):
+        b, c = r0["rec"][it], r1["rec"][it]
+        assert torch.equal(b["gflat"], c["gflat"]) and torch.equal(b["per"], c["per"]) and torch.equal(b["worst"], c["worst"])
+        assert b["per"].numel() == 8 and bool(torch.isfinite(b["gflat"]).all()) and float(b["gflat"].abs().max()) > 0
+    assert torch.equal(r0["flat"], r1["flat"])
+    assert bool(torch.isfinite(r0["pool"]).all()) and bool(torch.isfinite(r1["pool"]).all())
+    # two iterations of 4 local samples each touched at most 8 of the 16 slots of a shard; the others still hold seeds
+    for r in (r0, r1):
+        untouched = int(((r["pool"][:, :3].abs().sum(dim=(1, 2, 3)) == 0) & (r["pool"][:, 3].sum(dim=(1, 2)) == 1)).sum())
+        assert untouched >= 8
