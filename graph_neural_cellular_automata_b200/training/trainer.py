@@ -220,9 +220,9 @@ class GraphNCATrainer:
             if n_w > 0 or do_reseed:
                 hit = torch.zeros(Bg, dtype=torch.bool, device=self.device)
                 if n_w > 0:
-                    hit[worst] = True
-                if do_reseed:
-                    hit[rand_idx] = True
+                    hit.index_fill_(0, worst, True)      # (hit[worst] = True would stage the scalar through pageable
+                if do_reseed:                            #  memory: a hidden stream synchronisation per step)
+                    hit[rand_idx:rand_idx + 1].fill_(True)
                 mine = hit[sh.lo:sh.hi].view(-1, 1, 1, 1)
                 new_states = torch.where(mine, self.seed_fn(sh.local_batch), xT)
         else:
