@@ -64,7 +64,7 @@ if "--json" in opt:
     rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
     db[opt["--key"]] = {
         "report": os.path.basename(rep), "command": opt.get("--command", ""), "commit": commit,
-        "kernel_name": d.get("Kernel Name", ("", ""))[1][:80], "duration_us_under_ncu": num("gpu__time_duration.sum", 1e-3),
+        "kernel_name": d.get("Kernel Name", ("", ""))[1][:80], "duration_us_under_ncu": num("gpu__time_duration.sum"),
         "dram_bytes_per_launch": (rd or 0) + (wr or 0) if rd is not None else None,
         "fma_pipe_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
         "tensor_pipe_pct": num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
