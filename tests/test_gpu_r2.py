@@ -189,3 +189,42 @@ def test_bench_shape_forward_vs_reference(impl):
         xT = _skip_unsupported(impl, lambda: rollout(m, O.make_seed(16, 40, B).to(DEV), sched, impl=impl))
     assert rel_err(xT.cpu(), g["x_96"]) < 1e-5, rel_err(xT.cpu(), g["x_96"])
     assert torch.equal(GF.alive_mask(xT, 0.12).cpu(), O.alive_mask(T32(g["x_96"]), 0.12))
+
+
+def test_resident_training_path_is_bitwise_deterministic_at_bench_shape():
+    """Race evidence at the shape the training bench runs (compute-sanitizer is closed on this pool): the resident forward
+    with BPTT records + resident backward + batched weight gradients on the ragged B=32 case (4 waves of 8 clusters, T up to
+    80, in-kernel Philox) give bit-identical states, input gradients and parameter gradients run to run."""
+    x48 = T32(load_golden("graph_torus_rollout.npz")["x_48"])
+    x0 = torch.cat([O.make_seed(16, 40, 1) if b % 2 == 0 else x48[(b // 2) % 2:(b // 2) % 2 + 1] for b in range(32)], 0)
+    outs = []
+    for _ in range(3):
+        g, m, xT, per, gx = _grad_case("grads_ragged_b32.npz", x0, "resident", "philox")
+        outs.append((xT, gx, {n: p.grad.detach().cpu().clone() for n, p in m.named_parameters() if p.grad is not None}))
+    for xT, gx, pg in outs[1:]:
+        assert torch.equal(xT, outs[0][0]) and torch.equal(gx, outs[0][1])
+        assert all(torch.equal(pg[n], outs[0][2][n]) for n in pg)
+
+
+@pytest.mark.parametrize("C,Hh,B", [(16, 128, 20), (32, 64, 80)])
+def test_classic_model_on_the_tensor_core_path(C, Hh, B):
+    """The large-problem update kernel (k_update_tc: tcgen05, 3xTF32) without a graph term: classic NeuralCA, one step
+    against the oracle in fp64 (state 1e-5, alive mask bit-exact)."""
+    import random
+    torch.manual_seed(3); random.seed(3)
+    m = G.NeuralCA(C, update_hidden=128, img_size=Hh, update_gain=0.1, alpha_thr=0.1)
+    with torch.no_grad():
+        m.update_net[2].weight.normal_(0, 0.05)
+        m.norm.weight.uniform_(0.5, 1.5); m.norm.bias.normal_(0, 0.1)
+    p64 = {k: v.detach().clone().double() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    yy, xx = torch.meshgrid(torch.arange(Hh), torch.arange(Hh), indexing="ij")
+    disk = (((yy - Hh / 2) ** 2 + (xx - Hh / 2) ** 2) < (0.3 * Hh) ** 2).float()
+    x = torch.rand(B, C, Hh, Hh) * disk
+    fu = torch.rand(B, 1, Hh, Hh)
+    cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=False)
+    ref = O.nca_step(x.double(), p64, cfg, 0.5, fu.double(), ())
+    with torch.no_grad():
+        out = m.step(x.to(DEV), 0.5, fire_u=fu.to(DEV))
+    assert max_rel(out.cpu(), ref) < 1e-5, max_rel(out.cpu(), ref)
+    assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))
