@@ -41,7 +41,7 @@ constexpr int kMaxWords = kMaxRows * kMaxRows / 32;   // words of a linear cell 
 
 struct RepArgs {
   StepArgs s;
-  int T, NC, ucap, KP, listcap, HWp;
+  int T, NC, ucap, KP, listcap, HWp, zd;
   float inv_n;
   const float* fire_u_base;   // [T][B][H][W] or null
   const float* x0;
@@ -113,7 +113,11 @@ __device__ __forceinline__ uint32_t pack_nibbles(uint32_t nib, int lane) {
   return w;
 }
 
-template <int C>
+// ZP: zero-padded graph shift (the module default, graph_augmentation.py:85-92): senders (y - dy, x) -- the reference's
+// _shift2d_pad slices the x padding away again, so dx is a no-op -- and per-sample softmax weights over the k offsets
+// (graph_augmentation.py:114,136-154), recomputed from the resident state at the top of every step.  A separate
+// instantiation: the torus kernel (trainer, bench) is compiled exactly as before.
+template <int C, bool ZP>
 __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const float* __restrict__ packed) {
   static_assert(C == 16, "lane mapping: 2 cells x 16 channels per warp row");
   constexpr int C3 = 3 * C, HID = 128;
@@ -186,6 +190,19 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
   if (tid < C) { s_gbb[0][tid] = packed[P.gamma + tid]; s_gbb[1][tid] = packed[P.beta + tid]; s_gbb[2][tid] = graph ? packed[P.bm + tid] : 0.f; }
   const float wuni = k > 0 ? 1.0f / (float)k : 0.f;
   if (tid == 0) { float as = 0.f; for (int n = 0; n <= 16; ++n) { s_astab[n] = as; as += wuni; } }
+  // zero-padded shift: row sums of the state, pooled query / keys, softmax weights of the step
+  constexpr int kZD = ZP ? 32 : 1;                              // d_model <= 32
+  __shared__ float s_rowsum[ZP ? C : 1][ZP ? kMaxRows : 1];
+  __shared__ float s_zq[2][kZD][ZP ? C : 1];                    // Wq, Wk
+  __shared__ float s_zb[3][kZD];                                // bq, bk, (pooled query)
+  __shared__ float s_w[16];                                     // attention weight of offset i at this step
+  __shared__ float s_zscale;
+  const int zd = ZP ? R.zd : 0;
+  if constexpr (ZP) {
+    for (int i = tid; i < zd * C; i += kPT) { s_zq[0][i / C][i % C] = packed[P.wq + i]; s_zq[1][i / C][i % C] = packed[P.wk + i]; }
+    if (tid < zd) { s_zb[0][tid] = packed[P.bq + tid]; s_zb[1][tid] = packed[P.bk + tid]; }
+    if (tid == 0) s_zscale = fabsf(packed[P.scaling]) + 1e-6f;
+  }
   const size_t sample_off = (size_t)b * C * HW;
   // global [C][HW] <-> smem [cell][C]; lanes = 8 cells x 4 channels (32 B global sectors, 4-way smem conflict)
   auto store_item = [&](float* dst, int lo, int hi, int i) {
@@ -411,6 +428,60 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
     }
     const float gain_m = s_gain[cur];
     const bool msg_on = graph && gain_m != 0.f && k > 0;
+    if constexpr (ZP) {
+      if (msg_on) {
+        // per-(channel, row) sums of x_t from my replica (every CTA computes all of them: 25.6 k adds, no exchange)
+        for (int row = warp; row < H; row += kPW) {               // warp per row, lane = (cell parity, channel): 128-byte loads
+          const int c = lane & 15, hw = lane >> 4;
+          const float* p = (c == 3) ? (sAg + row * W) : (sX + (size_t)row * W * C + c);
+          const int st = (c == 3) ? 1 : C;
+          float s0 = 0.f, s1 = 0.f;                              // W % 4 == 0: cells hw, hw+2, hw+4, ... in two chains
+          for (int x = hw; x < W; x += 4) { s0 += p[x * st]; s1 += p[(x + 2) * st]; }
+          float sv = s0 + s1;
+          sv += __shfl_xor_sync(0xffffffffu, sv, 16);
+          if (lane < C) s_rowsum[c][row] = sv;
+        }
+        __syncthreads();
+        // one warp per offset (k <= 16 = the warps of the CTA): lanes c < C sum the kept rows, lane j forms its component
+        // of the pooled query (recomputed by every warp: 16 FMAs) and of the mean shifted key, one shuffle tree per offset
+        if (warp < k) {
+          const float invHW = 1.0f / (float)HW;
+          float xs_all = 0.f, ss = 0.f;
+          const int dy = (int)s_off[cur][2 * warp];
+          const int lo = max(0, -dy), hi = min(H, H - dy), nrows = max(0, hi - lo);
+          if (lane < C) {
+            for (int y = 0; y < H; ++y) xs_all += s_rowsum[lane][y];                 // pooled query (:114)
+            for (int y = lo; y < hi; ++y) ss += s_rowsum[lane][y];                   // dy-shifted, zero-filled K (:126,136-138)
+          }
+          float qp = 0.f, kp = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float xm = __shfl_sync(0xffffffffu, xs_all, c) * invHW, sc = __shfl_sync(0xffffffffu, ss, c);
+            if (lane < zd) { qp = fmaf(s_zq[0][lane][c], xm, qp); kp = fmaf(s_zq[1][lane][c], sc, kp); }
+          }
+          float li = 0.f;
+          if (lane < zd) {
+            qp += s_zb[0][lane];
+            kp = (kp + (float)nrows * (float)W * s_zb[1][lane]) * invHW;
+            li = qp * kp;
+          }
+          li = warp_sum(li);
+          if (lane == 0) s_w[warp] = li;                         // logit of offset `warp`
+        }
+        __syncthreads();
+        if (warp == 0) {                                         // softmax over the k offsets (:150-154)
+          const float logit = lane < k ? s_w[lane] : -INFINITY;
+          float mx = logit;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          const float e = lane < k ? expf((logit - mx) / s_zscale) : 0.f;
+          const float se = warp_sum(e);
+          __syncwarp();
+          if (lane < 16) s_w[lane] = lane < k ? e / se : 0.f;
+        }
+        __syncthreads();
+      }
+    }
     REP_MARK(0);
     if (R.dbg && tid == 0) s_dbg[8] += n_my;
     if (R.masks && rank == 0 && tid < NW) {
@@ -434,10 +505,17 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
             if (i < k) {
               const unsigned ent = s_list[min(slot0 + m, lim - 1)];
               int qy = (int)(ent >> 8) - (int)s_off[cur][2 * i], qx = (int)(ent & 255u) - (int)s_off[cur][2 * i + 1];
-              qy += qy < 0 ? H : 0; qy -= qy >= H ? H : 0;
-              qx += qx < 0 ? W : 0; qx -= qx >= W ? W : 0;
+              bool inside = true;
+              if constexpr (ZP) {
+                qx = (int)(ent & 255u);                          // dx is a no-op in the reference's zero-padded shift
+                inside = qy >= 0 && qy < H;
+                qy = inside ? qy : 0;
+              } else {
+                qy += qy < 0 ? H : 0; qy -= qy >= H ? H : 0;
+                qx += qx < 0 ? W : 0; qx -= qx >= W ? W : 0;
+              }
               const int qc = qy * W + qx;
-              if (!a2a || ((s_bAliveS[qc >> 5] >> (qc & 31)) & 1u)) q = (short)qc;
+              if (inside && (!a2a || ((s_bAliveS[qc >> 5] >> (qc & 31)) & 1u))) q = (short)qc;
             }
             myq[m * KP + i] = q;
           }
@@ -478,11 +556,17 @@ __global__ void __launch_bounds__(kPT, 1) k_rep_fwd(RepArgs R, Packed P, const f
               for (int j = 0; j < 8; ++j) vq[j] = pb[max(qs[j], 0) * st];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                xsv = fmaf(qs[j] >= 0 ? wuni : 0.f, vq[j], xsv);
-                nv += qs[j] >= 0;
+                if constexpr (ZP) {
+                  const float wj = qs[j] >= 0 ? s_w[o8 + j] : 0.f;
+                  xsv = fmaf(wj, vq[j], xsv);
+                  as += wj;
+                } else {
+                  xsv = fmaf(qs[j] >= 0 ? wuni : 0.f, vq[j], xsv);
+                  nv += qs[j] >= 0;
+                }
               }
             }
-            as = s_astab[nv];
+            if constexpr (!ZP) as = s_astab[nv];
           }
           xs[r] = xsv; asv[r] = as;
           if (R.rec && slot0 + m < lim) {          // forward half of the record (gnca_rep.h): y | u | xs | tanh(agg) | as
@@ -855,7 +939,8 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
   if (H > kMaxRows || W > kMaxRows || H < 1 || W < 4 || (W & 3)) return GNCA_ERR_UNSUPPORTED;   // quads of 4 cells per row
   if (H * W > 4 * kPT) return GNCA_ERR_UNSUPPORTED;                                            // one quad per thread
   const int k = graph ? sched.k : 0;
-  if (graph && k > 0 && !(m.flags & GNCA_F_TORUS)) return GNCA_ERR_UNSUPPORTED;     // zero-padded shift: streaming path
+  const bool zp = graph && k > 0 && !(m.flags & GNCA_F_TORUS);      // zero-padded shift: the ZP instantiation (forward only)
+  if (zp && (m.d_model > 32 || rec || masks)) return GNCA_ERR_UNSUPPORTED;      // BPTT records: torus only
   if (k > 16) return GNCA_ERR_UNSUPPORTED;
   if (sched.fire_u && ((uintptr_t)sched.fire_u & 15)) return GNCA_ERR_UNSUPPORTED;    // float4 loads of the uniforms
   if (k > 0 && (sched.max_offset <= 0 || sched.max_offset >= H || sched.max_offset >= W)) return GNCA_ERR_UNSUPPORTED;
@@ -877,6 +962,8 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
   R.rec = rec; R.masks = masks;
   R.damage = DamageView{sched.damage, sched.damage_layout}; R.damage_step = sched.damage_step;
   R.KP = k > 8 ? 16 : 8;
+  R.zd = zp ? m.d_model : 0;
+  const void* kfn = zp ? (const void*)k_rep_fwd<16, true> : (const void*)k_rep_fwd<16, false>;
   R.HWp = 4 * (((HW >> 2) + 31) & ~31) + 16;      // planes padded to whole warps of quads + one scratch quad
   R.inv_n = (float)(1.0 / ((double)C * (double)H * (double)W));
 
@@ -895,7 +982,7 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
       while (smem > 226 * 1024 && ucap > 128) { ucap -= 64; smem = rep_smem_bytes(C, HW, ucap, share); }
       if (smem > 226 * 1024) continue;
       if (ucap < share && !scratch) continue;
-      GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GNCA_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cudaLaunchConfig_t q{};
       q.gridDim = dim3(B * NC); q.blockDim = dim3(kPT); q.dynamicSmemBytes = smem; q.stream = st;
       cudaLaunchAttribute qa[1];
@@ -903,7 +990,7 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
       qa[0].val.clusterDim.x = NC; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       q.attrs = qa; q.numAttrs = 1;
       int ncl = 0;
-      if (cudaOccupancyMaxActiveClusters(&ncl, k_rep_fwd<16>, &q) != cudaSuccess || ncl < 1) {
+      if (cudaOccupancyMaxActiveClusters(&ncl, kfn, &q) != cudaSuccess || ncl < 1) {
         cudaGetLastError();
         continue;
       }
@@ -917,7 +1004,7 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
   R.u_over = scratch;
   R.over_cap = (HW + pick - 1) / pick + 1 > pick_ucap ? (HW + pick - 1) / pick + 1 - pick_ucap : 0;
   if ((size_t)pick * R.over_cap > (size_t)HW) return GNCA_ERR_UNSUPPORTED;   // scratch holds B*C*HW floats
-  GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_rep_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pick_smem));
+  GNCA_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pick_smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(B * pick);
   cfg.blockDim = dim3(kPT);
@@ -939,7 +1026,8 @@ int run_rep_fwd(const gnca_model& m, const Packed& P, const float* packed, int B
     R.dbg_cta = atoi(getenv("GNCA_PHASE_TIMING"));
   }
   prof_begin(PROF_RESIDENT_FWD, st);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_rep_fwd<16>, R, P, packed);
+  cudaError_t e = zp ? cudaLaunchKernelEx(&cfg, k_rep_fwd<16, true>, R, P, packed)
+                     : cudaLaunchKernelEx(&cfg, k_rep_fwd<16, false>, R, P, packed);
   prof_end(PROF_RESIDENT_FWD, st);
   if (e != cudaSuccess) return (int)e;
   GNCA_LAUNCH_CHECK();

@@ -225,3 +225,22 @@ def test_damage_descriptor_in_rollout(impl, kind):
         mid = rollout(m, x0, s1, impl="streaming")
         two = rollout(m, (mid * dense).contiguous(), s2, impl="streaming")
     assert rel_err(a.cpu(), two.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("impl", ["auto", "resident", "streaming"])
+def test_zeropad_rollout_matches_reference(impl):
+    """The MODULE DEFAULT graph shift (zero-padded: dy-only senders + per-sample softmax weights over the offsets,
+    graph_augmentation.py:85-92,136-154) through the rollout entry point: 12 reference steps from an aged state
+    (`graph_zeropad_rollout.npz`).  `auto` / `resident` run the ZP instantiation of the replicated cluster kernel, which
+    recomputes the attention weights from the resident state every step."""
+    g = load_golden("graph_zeropad_rollout.npz")
+    m = graph_model(False)
+    x0 = T32(g["x_0"]).to(DEV)
+    T = 12
+    sched = make_schedule(m, 2, 40, 40, T, fire_rate=float(g["fire_rate"]), offsets=[tup(c) for c in g["chosen"]],
+                          fire_u=T32(g["fire_u"]).to(DEV))
+    with torch.no_grad():
+        xT = _supported(impl, lambda: rollout(m, x0, sched, impl=impl))
+    ref = T32(g["x_12"])
+    assert rel_err(xT.cpu(), ref) < 1e-5, rel_err(xT.cpu(), ref)
+    assert torch.equal(GF.alive_mask(xT, 0.12).cpu(), O.alive_mask(ref, 0.12))
