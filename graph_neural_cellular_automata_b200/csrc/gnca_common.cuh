@@ -141,6 +141,7 @@ struct StepArgs {
   int nchunks, chunk;                 // k_update work split: cells per block and blocks per sample
   int npart;                          // GroupNorm partial slots per sample in `partials` (nchunks, or 3*nchunks: k_update_tc)
   const float* stats_ready;           // [B][2] (mean, rstd) already finished by the update path (k_update_tc2) or null
+  const uint32_t* actbits;            // [B][ceil(HW/32)] active (alive & fire) bits of this step written by k_compact, or null
   Offsets off;                        // host-supplied offsets (single step)
 };
 

@@ -194,8 +194,11 @@ struct UpdateSmem {
 constexpr int kMaxBalChunks = 1024;
 constexpr int kThreadsBal = 384;
 
+// actbits (optional): the active bit of every cell, one word per 32 consecutive cells -- k_apply reads them for its tile +
+// halo instead of recomputing alive_at (nine alpha loads) and the Philox draw of every halo cell
 template <int CH>
-__global__ void __launch_bounds__(kThreads) k_compact(StepArgs a, int C, uint16_t* __restrict__ glist, int* __restrict__ cnt) {
+__global__ void __launch_bounds__(kThreads) k_compact(StepArgs a, int C, uint16_t* __restrict__ glist, int* __restrict__ cnt,
+                                                      uint32_t* __restrict__ actbits = nullptr) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int H = a.H, W = a.W, HW = H * W;
   __shared__ int swcount[kThreads / 32], swbase[kThreads / 32 + 1];
@@ -217,6 +220,8 @@ __global__ void __launch_bounds__(kThreads) k_compact(StepArgs a, int C, uint16_
     }
     bal[it] = __ballot_sync(0xffffffffu, act);
     n += __popc(bal[it]);
+    if (actbits && lane == 0 && cell0 + warp * kPerWarp + it * 32 < HW)
+      actbits[(size_t)b * ((HW + 31) >> 5) + ((cell0 + warp * kPerWarp + it * 32) >> 5)] = bal[it];
   }
   if (lane == 0) swcount[warp] = n;
   __syncthreads();
@@ -507,7 +512,8 @@ __global__ void __launch_bounds__(kThreads) k_apply(StepArgs a, Packed P, const 
     unsigned char act = 0;
     if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
       const int cell = yy * W + xx;
-      act = alive_at(alpha, yy, xx, H, W, a.alpha_thr) && fires(a, fr, b, cell);
+      act = a.actbits ? (unsigned char)((a.actbits[(size_t)b * ((HW + 31) >> 5) + (cell >> 5)] >> (cell & 31)) & 1u)
+                      : (unsigned char)(alive_at(alpha, yy, xx, H, W, a.alpha_thr) && fires(a, fr, b, cell));
       const float uu = act ? u3[cell] : 0.f;
       v = updated_alpha(alpha[cell], act, uu, s_sc[3], s_bi[3], s_idle[3], a.update_gain);
     }
@@ -630,6 +636,7 @@ FwdWorkspace carve_fwd_workspace(void* base, const gnca_model& m, int B, int H, 
   ws.attn_w = reinterpret_cast<float*>(p + o); o = align_up(o + (size_t)B * GNCA_MAX_K * sizeof(float), 256);
   ws.absmean = reinterpret_cast<float*>(p + o); o = align_up(o + (size_t)B * H * W * sizeof(float), 256);
   ws.tc2 = p + o; o = align_up(o + update_tc2_workspace_bytes(B, H, W), 256);
+  ws.actbits = reinterpret_cast<uint32_t*>(p + o); o = align_up(o + (size_t)B * ((H * W + 31) / 32) * sizeof(uint32_t), 256);
   ws.bytes = o;
   return ws;
 }
@@ -655,6 +662,7 @@ static int launch_update(const gnca_model& m, const Packed& P, const float* pack
   const size_t smem = UpdateSmem<C>::bytes(m.hidden, graph);
   dim3 g1(a.nchunks, a.B);
   a.stats_ready = nullptr;
+  a.actbits = nullptr;
   if (a.chunk == kChunkSmall) {
     a.npart = a.nchunks;
     GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -681,7 +689,8 @@ static int launch_update(const gnca_model& m, const Packed& P, const float* pack
     int* cnt = reinterpret_cast<int*>(reinterpret_cast<char*>(ws.partials) + used);
     int* prefix = cnt + (size_t)a.B * a.nchunks;
     uint16_t* glist = reinterpret_cast<uint16_t*>(ws.absmean);
-    k_compact<kChunk><<<g1, kThreads, 0, st>>>(a, C, glist, cnt);
+    k_compact<kChunk><<<g1, kThreads, 0, st>>>(a, C, glist, cnt, ws.actbits);
+    a.actbits = ws.actbits;
     k_scan<<<a.B, 32, 0, st>>>(a.nchunks, cnt, prefix);
     if (use_tc) {
       g_launches += 2;

@@ -11,6 +11,7 @@ struct FwdWorkspace {
   float* attn_w;      // [B][MAX_K]
   float* absmean;     // [B][H][W]
   void* tc2;          // tile masks / lists / partials of k_update_tc2 (update_tc2_workspace_bytes)
+  uint32_t* actbits;  // [B][ceil(HW/32)] active bits of the step (k_compact -> k_apply)
   size_t bytes;
 };
 
