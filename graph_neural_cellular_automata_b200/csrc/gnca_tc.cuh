@@ -95,6 +95,14 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   hi = tf32_rna(x);
   lo = tf32_rna(x - __uint_as_float(hi));
 }
+// activation split of the tile kernels, 3 instructions instead of the 7 `cvt.rna.tf32` expands to twice on sm_100a:
+// hi = x rounded to nearest (ties away) on the 13 dropped bits by an integer add + mask (finite x; an overflow rounds to
+// inf like the cvt), lo = x - hi handed to the tensor core as it is -- the unit truncates its operands to tf32, and
+// |lo| <= 2^-11 |x|, so the truncation of lo costs <= 2^-21 |x| (the cvt version 2^-22; the dropped lo*lo term 2^-22).
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
 
 // named barriers (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }

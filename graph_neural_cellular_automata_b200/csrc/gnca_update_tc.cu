@@ -32,7 +32,114 @@ constexpr int kTcThreads = kTcWG * 128;
 constexpr int kTcRange = 1152;              // active cells (ranks) per unit = 3 rounds of 384; >= kTcChunk
 constexpr int kTcHid = 128;
 constexpr int kBarTurn = 1;                 // named barriers 1..3: the tensor-chain token of warpgroup g
+constexpr int kTcNB = 4;                    // channels per batch of perception loads (36 in flight per thread)
 constexpr int kBarWg = 4;                   // named barriers 4..6: warpgroup-local sync
+
+
+// ---- latency-tolerant gathers of the tile kernel ------------------------------------------------------------------------
+// The generic `perceive` / `gather_senders` of gnca_common.cuh compile to one basic block per channel / sender (the edge
+// predicates become branches), so a warp has at most 9 loads in flight and pays one L2 round trip per channel: 30 k
+// cycles per 128-cell tile each (profiles/r02_k_update_tc2.md).  The two functions below request NB channels x 9 taps
+// (perception) or two senders' alive windows + all their channels (message) before the first use, without branches.
+
+// perception of one cell, same arithmetic as perceive<C> (perception.py:21-26): the taps beyond a grid edge are read
+// from a clamped (valid) address and replaced by the zero halo with a select
+template <int C, int NB>
+__device__ __forceinline__ void perceive_batched(const float* __restrict__ xs, int y, int x, int H, int W,
+                                                 float (&out)[3 * C]) {
+  static_assert(C % NB == 0, "channel batches");
+  const int HW = H * W;
+  const bool up = y > 0, dn = y < H - 1, lf = x > 0, rt = x < W - 1;
+  const int oU = up ? -W : 0, oD = dn ? W : 0, oL = lf ? -1 : 0, oR = rt ? 1 : 0;
+  const float* __restrict__ p = xs + y * W + x;
+#pragma unroll
+  for (int c0 = 0; c0 < C; c0 += NB) {
+    float v[NB][9];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+      const float* pc = p + (size_t)(c0 + n) * HW;
+      v[n][0] = __ldg(pc + (oU + oL)); v[n][1] = __ldg(pc + oU); v[n][2] = __ldg(pc + (oU + oR));
+      v[n][3] = __ldg(pc + oL);        v[n][4] = __ldg(pc);      v[n][5] = __ldg(pc + oR);
+      v[n][6] = __ldg(pc + (oD + oL)); v[n][7] = __ldg(pc + oD); v[n][8] = __ldg(pc + (oD + oR));
+    }
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+      const int c = c0 + n;
+      const float a00 = (up && lf) ? v[n][0] : 0.f, a01 = up ? v[n][1] : 0.f, a02 = (up && rt) ? v[n][2] : 0.f;
+      const float a10 = lf ? v[n][3] : 0.f, a12 = rt ? v[n][5] : 0.f;
+      const float a20 = (dn && lf) ? v[n][6] : 0.f, a21 = dn ? v[n][7] : 0.f, a22 = (dn && rt) ? v[n][8] : 0.f;
+      out[c] = v[n][4];
+      out[C + c] = (a00 - a02) + 2.f * (a10 - a12) + (a20 - a22);
+      out[2 * C + c] = (a00 + 2.f * a01 + a02) - (a20 + 2.f * a21 + a22);
+    }
+  }
+}
+
+// xs / as of gather_senders<C> (graph_augmentation.py:104-158), two senders per round, straight-line: the offsets
+// (reduced modulo the grid) and weights of the step wait in shared memory, all channels of both senders are requested
+// first, then their 3x3 alive windows (edge taps clamped into the window: a duplicate never changes a max), and only then
+// is anything consumed.  A sender that is out of range or not alive contributes with weight 0 (fmaf(0, finite, acc) ==
+// acc: the bits of the generic function's `continue`).
+template <int C>
+__device__ __forceinline__ void gather_senders_pairs(const StepArgs& a, const float* __restrict__ xs_base, int y, int x,
+                                                     const int* __restrict__ s_dy, const int* __restrict__ s_dx,
+                                                     const float* __restrict__ s_wt, float (&xs)[C], float& as) {
+  const int H = a.H, W = a.W, HW = H * W, k = a.k;
+  const bool torus = (a.flags & GNCA_F_TORUS) != 0, A2A = (a.flags & GNCA_F_ALIVE_TO_ALIVE) != 0;
+  const float* __restrict__ alpha = xs_base + 3 * HW;
+#pragma unroll
+  for (int c = 0; c < C; ++c) xs[c] = 0.f;
+  as = 0.f;
+#pragma unroll 1
+  for (int i = 0; i < k; i += 2) {
+    float w[2], v[2][C], al[2][9] = {};
+    int qy[2], qx[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int ii = min(i + s, k - 1);
+      const int dy = s_dy[ii], dx = s_dx[ii];
+      int yy = y - dy, xx = torus ? x - dx : x;
+      bool ok = i + s < k;
+      if (torus) {
+        yy = yy < 0 ? yy + H : (yy >= H ? yy - H : yy);
+        xx = xx < 0 ? xx + W : (xx >= W ? xx - W : xx);
+      } else {
+        ok = ok && yy >= 0 && yy < H;
+        yy = ok ? yy : y;
+      }
+      qy[s] = yy; qx[s] = xx;
+      w[s] = ok ? s_wt[ii] : 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const float* qp = xs_base + (qy[s] * W + qx[s]);
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[s][c] = __ldg(qp + (size_t)c * HW);
+    }
+    if (A2A) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int ru = (qy[s] > 0 ? qy[s] - 1 : qy[s]) * W, rc = qy[s] * W, rd = (qy[s] < H - 1 ? qy[s] + 1 : qy[s]) * W;
+        const int xl = qx[s] > 0 ? qx[s] - 1 : qx[s], xc = qx[s], xr = qx[s] < W - 1 ? qx[s] + 1 : qx[s];
+        al[s][0] = __ldg(alpha + ru + xl); al[s][1] = __ldg(alpha + ru + xc); al[s][2] = __ldg(alpha + ru + xr);
+        al[s][3] = __ldg(alpha + rc + xl); al[s][4] = __ldg(alpha + rc + xc); al[s][5] = __ldg(alpha + rc + xr);
+        al[s][6] = __ldg(alpha + rd + xl); al[s][7] = __ldg(alpha + rd + xc); al[s][8] = __ldg(alpha + rd + xr);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      float ww = w[s];
+      if (A2A) {
+        const float m = fmaxf(fmaxf(fmaxf(fmaxf(al[s][0], al[s][1]), fmaxf(al[s][2], al[s][3])),
+                                    fmaxf(fmaxf(al[s][4], al[s][5]), fmaxf(al[s][6], al[s][7]))), al[s][8]);
+        ww = m > a.graph_alpha_thr ? ww : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) xs[c] = fmaf(ww, v[s][c], xs[c]);
+      as += ww;
+    }
+  }
+}
 
 template <int C>
 struct TcCols {                             // TMEM column map of the CTA's single tile pipeline
@@ -47,7 +154,7 @@ template <int C>
 static size_t tc_smem_bytes(int nchunks, bool graph) {
   size_t f = (size_t)2 * kTcHid * 3 * C + (size_t)2 * C * kTcHid + kTcHid + (graph ? C * C + C : 0);
   return f * sizeof(float) + kTcWG * 4 * 2 * sizeof(double) + kTcWG * sizeof(uint64_t) + 2 * sizeof(uint32_t) +
-         (size_t)kTcWG * (nchunks + 1) * sizeof(int) + 128;
+         (size_t)kTcWG * (nchunks + 1) * sizeof(int) + (graph ? (size_t)kTcWG * (C * 128 + 3 * GNCA_MAX_K) * sizeof(float) : 0) + 128;
 }
 
 template <int C>
@@ -71,6 +178,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sred + kTcWG * 4 * 2);  // [3]
   uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + kTcWG);
   int* s_pf = reinterpret_cast<int*>(tslot + 2) + g * (nchunks + 1);   // this warpgroup's prefix table
+  // the tile's message waits here ([c][t], conflict-free) while perception and the tensor chain need the registers
+  float* s_msg0 = reinterpret_cast<float*>(reinterpret_cast<int*>(tslot + 2) + kTcWG * (nchunks + 1));
+  float* s_msg = s_msg0 + (size_t)g * C * 128 + t;
+  // this warpgroup's copy of the step's sender offsets (reduced modulo the grid) and of the sample's attention weights
+  int* s_dy = reinterpret_cast<int*>(s_msg0 + (size_t)kTcWG * C * 128) + g * 3 * GNCA_MAX_K;
+  int* s_dx = s_dy + GNCA_MAX_K;
+  float* s_wt = reinterpret_cast<float*>(s_dx + GNCA_MAX_K);
 
   block_copy(sW1, packed + P.w1c, 2 * kTcHid * K1);
   block_copy(sW2, packed + P.w2c, 2 * C * kTcHid);
@@ -121,6 +235,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
     }
     const int r_hi = min(r_lo + kTcRange, total);
     for (int i = t; i <= nchunks; i += 128) s_pf[i] = __ldg(pf + i);
+    if (do_msg && t < a.k) {
+      int dy, dx;
+      step_offset(a, t, dy, dx);
+      const bool torus = (a.flags & GNCA_F_TORUS) != 0;
+      s_dy[t] = torus ? dy % H : dy; s_dx[t] = torus ? dx % W : 0;
+      s_wt[t] = a.attn_w ? __ldg(a.attn_w + (size_t)b * a.k + t) : 1.0f / (float)a.k;
+    }
     bar_sync(kBarWg + g, 128);
     const float* xs_base = a.x_in + (size_t)b * C * HW;
     float s1 = 0.f, s2 = 0.f;
@@ -135,23 +256,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
       const int cy = cell >= 0 ? cell / W : 0, cx = cell >= 0 ? cell - cy * W : 0;
       TC_MARK(0);
       // ---- graph message (CUDA cores; graph_augmentation.py:104-169 by linearity, ncagraph.py:94-104,141) ----------
-      float msg[C];
+      if (do_msg) {
+        if (cell >= 0) {
+          float xsnd[C], as;
+          gather_senders_pairs<C>(a, xs_base, cy, cx, s_dy, s_dx, s_wt, xsnd, as);
+          // agg = Wm xs + bm as (msg_proj by linearity), message = gain * tanh(agg) on the updated channels
+          // (ncagraph.py:94-104,141): a rolled loop over quads of output channels keeps the kernel's code inside the
+          // instruction cache
+#pragma unroll 1
+          for (int c4 = 0; c4 < C; c4 += 4) {
+            const float4 bq = *reinterpret_cast<const float4*>(sbm + c4);
+            float g0 = bq.x * as, g1 = bq.y * as, g2 = bq.z * as, g3 = bq.w * as;
 #pragma unroll
-      for (int c = 0; c < C; ++c) msg[c] = 0.f;
-      if (do_msg && cell >= 0) {
-        float xsnd[C], as;
-        gather_senders<C>(a, xs_base, b, cy, cx, xsnd, as);
-        float agg[C];
-        msg_project<C>(xsnd, as, sWmT, sbm, agg);
-#pragma unroll
-        for (int c = 0; c < C; ++c) msg[c] = c >= c_lo ? tanhf(agg[c]) * gain_m : 0.f;
+            for (int ci = 0; ci < C; ++ci) {
+              const float4 wq = *reinterpret_cast<const float4*>(sWmT + ci * C + c4);
+              g0 = fmaf(wq.x, xsnd[ci], g0); g1 = fmaf(wq.y, xsnd[ci], g1);
+              g2 = fmaf(wq.z, xsnd[ci], g2); g3 = fmaf(wq.w, xsnd[ci], g3);
+            }
+            s_msg[(c4 + 0) * 128] = c4 + 0 >= c_lo ? tanhf(g0) * gain_m : 0.f;
+            s_msg[(c4 + 1) * 128] = c4 + 1 >= c_lo ? tanhf(g1) * gain_m : 0.f;
+            s_msg[(c4 + 2) * 128] = c4 + 2 >= c_lo ? tanhf(g2) * gain_m : 0.f;
+            s_msg[(c4 + 3) * 128] = c4 + 3 >= c_lo ? tanhf(g3) * gain_m : 0.f;
+          }
+        }
       }
       TC_MARK(1);
       // ---- perception (perception.py:21-26) --------------------------------------------------------------------------
       float yv[K1];
-      if (cell >= 0) {
-        perceive<C>(xs_base, cy, cx, H, W, yv);
-      } else {
+      perceive_batched<C, kTcNB>(xs_base, cy, cx, H, W, yv);      // an idle lane reads the window of cell 0 and drops it
+      if (cell < 0) {
 #pragma unroll
         for (int k = 0; k < K1; ++k) yv[k] = 0.f;
       }
@@ -164,7 +297,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
       for (int c0 = 0; c0 < K1; c0 += 16) {
         uint32_t vh[16], vl[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) split_tf32(yv[c0 + q], vh[q], vl[q]);
+        for (int q = 0; q < 16; ++q) split_tf32_fast(yv[c0 + q], vh[q], vl[q]);
         tmem_st16(tYh + lane_base + c0, vh);
         tmem_st16(tYl + lane_base + c0, vl);
       }
@@ -185,7 +318,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
       }
       mbar_wait(my_bar, parity); parity ^= 1;
       fence_after();
-#pragma unroll
+#pragma unroll 2
       for (int c0 = 0; c0 < kTcHid; c0 += 16) {                 // epilogue 1: + b1, ReLU (update_net.1), split, back to TMEM
         uint32_t v[16], vl[16];
         tmem_ld16(tD1 + lane_base + c0, v);
@@ -194,7 +327,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const float h = fmaxf((__uint_as_float(v[q]) + __uint_as_float(vl[q])) + sb1[c0 + q], 0.f);
-          split_tf32(h, v[q], vl[q]);
+          split_tf32_fast(h, v[q], vl[q]);
         }
         tmem_st16(tD1 + lane_base + c0, v);
         tmem_st16(tHl + lane_base + c0, vl);
@@ -234,7 +367,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
         float* up = a.u + (size_t)b * C * HW + cell;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const float v = dxv[c] + msg[c];
+          const float v = dxv[c] + (do_msg ? s_msg[c * 128] : 0.f);
           up[(size_t)c * HW] = v;
           s1 += v;
           s2 = fmaf(v, v, s2);

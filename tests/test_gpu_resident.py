@@ -178,3 +178,43 @@ def test_batch_larger_than_any_cluster_split():
     m = graph_model(True)
     x0 = _grown_state(m, 80, 40, 40, steps=14, seed=4)
     _compare(m, x0, _sched(m, 80, 40, 40, 3, seed=22))
+
+
+def test_banded_kernel_32_channels_vs_oracle():
+    """40x40x32: the replicated-state kernel takes C = 16 only (a 40x40x32 replica is 205 KB), so the
+    `resident` implementation runs the banded cluster kernel (gnca_resident.cu, k_resident_fwd<32>).  10 steps from
+    ragged blobs against the fp64 oracle fed the same uniforms and offsets, and against the streaming kernels."""
+    torch.manual_seed(11); random.seed(11)
+    C, H, W, B, T = 32, 40, 40, 3, 10
+    m = G.NeuralCAGraph(C, update_hidden=128, img_size=H, update_gain=0.1, alpha_thr=0.1, message_gain=0.3,
+                        hidden_only=True, graph_zero_padded_shift=False)
+    with torch.no_grad():
+        m.update_net[2].weight.normal_(0, 0.05)
+        m.norm.weight.uniform_(0.5, 1.5); m.norm.bias.normal_(0, 0.1)
+    p = {k: v.detach().double() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    disk = (((yy - 19) ** 2 + (xx - 21) ** 2) < 11 ** 2).float()
+    x0 = torch.rand(B, C, H, W) * disk
+    x0[1, 3] *= (torch.rand(H, W) > 0.4).float()
+    fu = torch.rand(T, B, H, W)
+    chosen = [random.sample(m.graph.offsets, 8) for _ in range(T)]
+    frs = [0.5 + 0.04 * t for t in range(T)]
+    gains = [0.3 if t % 3 != 1 else 0.0 for t in range(T)]
+    sched = make_schedule(m, B, H, W, T, fire_rate=frs, fire_u=fu.to(DEV), offsets=chosen, message_gains=gains)
+    with torch.no_grad():
+        os.environ["GNCA_DEBUG"] = "1"
+        try:
+            res = rollout(m, x0.to(DEV), sched, impl="resident")
+        finally:
+            os.environ.pop("GNCA_DEBUG", None)
+        stream = rollout(m, x0.to(DEV), sched, impl="streaming")
+    ref = x0.double()
+    for t in range(T):
+        cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=True, message_gain=gains[t], hidden_only=True,
+                           zero_padded_shift=False)
+        ref = O.nca_step(ref, p, cfg, frs[t], fu[t].unsqueeze(1).double(), chosen[t])
+    assert rel_err(res.cpu(), ref.float()) < 1e-5, rel_err(res.cpu(), ref.float())
+    assert rel_err(stream.cpu(), ref.float()) < 1e-5
+    assert torch.equal(GF.alive_mask(res, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))
+    assert rel_err(res.cpu(), stream.cpu()) < 2e-6
