@@ -47,6 +47,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         objs.append(obj)
         extra = ["-DGNCA_PHASE_COUNTERS"] if os.environ.get("GNCA_PHASE_COUNTERS") else []
+        extra += [f"-D{d}" for d in os.environ.get("GNCA_EXTRA_DEFINES", "").split()]      # development experiments
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", path, "-o", obj]
         if verbose:
             print("[gnca build]", " ".join(cmd), flush=True)

@@ -245,14 +245,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
     bar_sync(kBarWg + g, 128);
     const float* xs_base = a.x_in + (size_t)b * C * HW;
     float s1 = 0.f, s2 = 0.f;
+    // rank -> cell: binary search in the chunk prefix table, then the chunk's list; done one tile ahead (the list entry
+    // arrives during the tensor chain)
+    auto locate = [&](int rank) -> int {
+      if (rank >= r_hi) return -1;
+      int lo = 0, hi = nchunks;                                 // s_pf[lo] <= rank < s_pf[hi]
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pf[mid] <= rank) lo = mid; else hi = mid; }
+      return lo * kTcChunk + (int)__ldg(glist + (size_t)b * HW + (size_t)lo * kTcChunk + (rank - s_pf[lo]));
+    };
+    int cell_next = locate(r_lo + g * 128 + t);
     for (int base = r_lo; base < r_hi; base += kTcThreads) {
-      const int rank = base + g * 128 + t;
-      int cell = -1;
-      if (rank < r_hi) {
-        int lo = 0, hi = nchunks;                               // s_pf[lo] <= rank < s_pf[hi]
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pf[mid] <= rank) lo = mid; else hi = mid; }
-        cell = lo * kTcChunk + (int)glist[(size_t)b * HW + (size_t)lo * kTcChunk + (rank - s_pf[lo])];
-      }
+      const int cell = cell_next;
       const int cy = cell >= 0 ? cell / W : 0, cx = cell >= 0 ? cell - cy * W : 0;
       TC_MARK(0);
       // ---- graph message (CUDA cores; graph_augmentation.py:104-169 by linearity, ncagraph.py:94-104,141) ----------
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
       }
       // ================= tensor-core chain: one warpgroup at a time ===================================================
       TC_MARK(2);
+      cell_next = locate(base + kTcThreads + g * 128 + t);
       bar_sync(kBarTurn + g, 256);
       fence_after();
       TC_MARK(3);
@@ -365,9 +369,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
       // ================================================================================================================
       if (cell >= 0) {
         float* up = a.u + (size_t)b * C * HW + cell;
+        if (do_msg) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) dxv[c] += s_msg[c * 128];
+        }
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const float v = dxv[c] + (do_msg ? s_msg[c * 128] : 0.f);
+          const float v = dxv[c];
           up[(size_t)c * HW] = v;
           s1 += v;
           s2 = fmaf(v, v, s2);
