@@ -549,21 +549,40 @@ __global__ void __launch_bounds__(kBThreads) k_bwd_mlp(BwdArgs A, Packed P, int 
             for (int c = 0; c < C; ++c) gb = fmaf(sbm[c], GAt[c * NBP + cl], gb);
             GB[cl] = gb;
           }
-          __syncthreads();
-          for (int oi = threadIdx.x; oi < a.k; oi += kBThreads) {
-            int dy, dx;
-            step_offset(a, oi, dy, dx);
-            float acc = 0.f;
-            for (int cl = 0; cl < nb; ++cl) {
-              const int pc = scell[cl], py = pc / W, px = pc - py * W;
-              int qy, qx;
-              if (!sender_of(py, px, dy, dx, H, W, torus, qy, qx)) continue;
-              if (a2a && !alive_at(xs_base + 3 * HW, qy, qx, H, W, a.graph_alpha_thr)) continue;
-              float v = GB[cl];
-              for (int c = 0; c < C; ++c) v = fmaf(GXSt[c * NBP + cl], __ldg(xs_base + (size_t)c * HW + qy * W + qx), v);
-              acc += v;
+          __syncthreads();        // GB / GXSt are complete and every thread is past (c3): Ht is free until the next batch
+          // one (receiver, offset) pair per thread -- 8 threads walking 64 receivers each with two dependent global
+          // round trips per receiver held the whole block at a barrier for ~100 k cycles --, then the same fixed-order
+          // sum over the receivers as before (a skipped pair adds an exact 0)
+          float* PV = Ht;         // [kcap][NB] over Ht | GHt (2 * hid * NBP floats)
+          const int kcap = (2 * hid * NBP) / NB;
+          for (int o0 = 0; o0 < a.k; o0 += kcap) {
+            const int kc = min(kcap, a.k - o0);
+            for (int idx = threadIdx.x; idx < kc * NB; idx += kBThreads) {
+              const int cl = idx % NB, oi = o0 + idx / NB;
+              float v = 0.f;
+              if (cl < nb) {
+                int dy, dx, qy, qx;
+                step_offset(a, oi, dy, dx);
+                const int pc = scell[cl], py = pc / W, px = pc - py * W;
+                if (sender_of(py, px, dy, dx, H, W, torus, qy, qx) &&
+                    !(a2a && !alive_at(xs_base + 3 * HW, qy, qx, H, W, a.graph_alpha_thr))) {
+                  float xq[C];
+#pragma unroll
+                  for (int c = 0; c < C; ++c) xq[c] = __ldg(xs_base + (size_t)c * HW + qy * W + qx);
+                  v = GB[cl];
+#pragma unroll
+                  for (int c = 0; c < C; ++c) v = fmaf(GXSt[c * NBP + cl], xq[c], v);
+                }
+              }
+              PV[idx] = v;
             }
-            A.gw_part[((size_t)b * A.nchunks + chunk) * GNCA_MAX_K + oi] += acc;
+            __syncthreads();
+            for (int oi = threadIdx.x; oi < kc; oi += kBThreads) {
+              float acc = 0.f;
+              for (int cl = 0; cl < nb; ++cl) acc += PV[oi * NB + cl];
+              A.gw_part[((size_t)b * A.nchunks + chunk) * GNCA_MAX_K + o0 + oi] += acc;
+            }
+            if (o0 + kcap < a.k) __syncthreads();
           }
         }
       }

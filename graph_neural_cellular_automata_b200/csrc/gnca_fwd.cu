@@ -102,63 +102,74 @@ __global__ void k_rowsum(int BCH, int W, const float* __restrict__ x, float* __r
   if ((threadIdx.x & 31) == 0) rs[row] = s;
 }
 
-// one block per sample; blockDim = 128.  Writes attn_w[b][k] and (optionally) logits for the backward.
+// one block per sample; blockDim = 128.  Writes attn_w[b][k].  The sample's row sums are staged in shared memory once
+// (stage != 0; the serial `s += rs[..]` chains over global memory cost 20 us per launch at 40x40x16) and the (offset,
+// channel) / (offset, feature) pairs run in parallel; every sum keeps its sequential order.
 __global__ void k_attn_weights(StepArgs a, Packed P, int C, int d, const float* __restrict__ packed,
-                               const float* __restrict__ rowsum, float* __restrict__ attn_w) {
+                               const float* __restrict__ rowsum, float* __restrict__ attn_w, int stage) {
   extern __shared__ float sm[];
-  const int b = blockIdx.x, H = a.H, W = a.W;
+  const int b = blockIdx.x, H = a.H, W = a.W, k = a.k;
   float* xsum = sm;            // [C]
   float* qp = xsum + C;        // [d]
-  float* ssum = qp + d;        // [C]
-  float* kp = ssum + C;        // [d]
-  float* logit = kp + d;       // [k]
+  float* S = qp + d;           // [k][C] row-range sums
+  float* KP = S + k * C;       // [k][d]
+  float* logit = KP + k * d;   // [k]
+  int* rlo = reinterpret_cast<int*>(logit + k);   // [k]
+  int* rhi = rlo + k;                              // [k]
+  float* rss = reinterpret_cast<float*>(rhi + k);  // [C][H] when staged
   const float* rs = rowsum + (size_t)b * C * H;
   const float invHW = 1.0f / (float)(H * W);
   const bool torus = (a.flags & GNCA_F_TORUS) != 0;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int y = 0; y < H; ++y) s += rs[c * H + y];
-    xsum[c] = s;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (stage) {
+    for (int i = tid; i < C * H; i += nt) rss[i] = rs[i];
+    rs = rss;
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < d; j += blockDim.x) {
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s = fmaf(packed[P.wq + j * C + c], xsum[c] * invHW, s);
-    qp[j] = s + packed[P.bq + j];
-  }
-  __syncthreads();
-  for (int i = 0; i < a.k; ++i) {
+  for (int i = tid; i < k; i += nt) {
     int dy, dx;
     step_offset(a, i, dy, dx);
     int lo = 0, hi = H;
     if (!torus) { lo = max(0, -dy); hi = min(H, H - dy); }
-    const int nrows = max(0, hi - lo);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float s = 0.f;
-      for (int y = lo; y < hi; ++y) s += rs[c * H + y];
-      ssum[c] = s;
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < d; j += blockDim.x) {
-      float s = 0.f;
-      for (int c = 0; c < C; ++c) s = fmaf(packed[P.wk + j * C + c], ssum[c], s);
-      kp[j] = (s + (float)nrows * (float)W * packed[P.bk + j]) * invHW;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float s = 0.f;
-      for (int j = 0; j < d; ++j) s = fmaf(qp[j], kp[j], s);
-      logit[i] = s;
-    }
-    __syncthreads();
+    rlo[i] = lo; rhi[i] = max(lo, hi);
   }
-  if (threadIdx.x == 0) {
+  __syncthreads();
+  for (int c = tid; c < C; c += nt) {
+    float s = 0.f;
+    for (int y = 0; y < H; ++y) s += rs[c * H + y];
+    xsum[c] = s;
+  }
+  for (int idx = tid; idx < k * C; idx += nt) {
+    const int i = idx / C, c = idx - i * C;
+    float s = 0.f;
+    for (int y = rlo[i]; y < rhi[i]; ++y) s += rs[c * H + y];
+    S[idx] = s;
+  }
+  __syncthreads();
+  for (int j = tid; j < d; j += nt) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(packed[P.wq + j * C + c], xsum[c] * invHW, s);
+    qp[j] = s + packed[P.bq + j];
+  }
+  for (int idx = tid; idx < k * d; idx += nt) {
+    const int i = idx / d, j = idx - i * d;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(packed[P.wk + j * C + c], S[i * C + c], s);
+    KP[idx] = (s + (float)(rhi[i] - rlo[i]) * (float)W * packed[P.bk + j]) * invHW;
+  }
+  __syncthreads();
+  for (int i = tid; i < k; i += nt) {
+    float s = 0.f;
+    for (int j = 0; j < d; ++j) s = fmaf(qp[j], KP[i * d + j], s);
+    logit[i] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
     float mx = -INFINITY;
-    for (int i = 0; i < a.k; ++i) mx = fmaxf(mx, logit[i]);
+    for (int i = 0; i < k; ++i) mx = fmaxf(mx, logit[i]);
     const float denom = fabsf(packed[P.scaling]) + 1e-6f;
     float se = 0.f;
-    for (int i = 0; i < a.k; ++i) { float e = expf((logit[i] - mx) / denom); logit[i] = e; se += e; }
-    for (int i = 0; i < a.k; ++i) attn_w[(size_t)b * a.k + i] = logit[i] / se;
+    for (int i = 0; i < k; ++i) { float e = expf((logit[i] - mx) / denom); logit[i] = e; se += e; }
+    for (int i = 0; i < k; ++i) attn_w[(size_t)b * k + i] = logit[i] / se;
   }
 }
 
@@ -168,8 +179,10 @@ int run_attn_prepass(const gnca_model& m, const Packed& P, const float* packed, 
   const int rows = a.B * m.C * a.H;
   k_rowsum<<<(rows + 7) / 8, 256, 0, st>>>(rows, a.W, a.x_in, ws.rowsum);
   GNCA_LAUNCH_CHECK();
-  const size_t sm = (size_t)(2 * m.C + 2 * m.d_model + a.k + 4) * sizeof(float);
-  k_attn_weights<<<a.B, 128, sm, st>>>(a, P, m.C, m.d_model, packed, ws.rowsum, ws.attn_w);
+  const int stage = (size_t)m.C * a.H * sizeof(float) <= 32 * 1024;
+  const size_t sm = (size_t)(m.C + m.d_model + a.k * (m.C + m.d_model) + 3 * a.k + 4 + (stage ? m.C * a.H : 0)) * sizeof(float);
+  if (sm > 48 * 1024) GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_attn_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_attn_weights<<<a.B, 128, sm, st>>>(a, P, m.C, m.d_model, packed, ws.rowsum, ws.attn_w, stage);
   GNCA_LAUNCH_CHECK();
   a.attn_w = ws.attn_w;
   return 0;

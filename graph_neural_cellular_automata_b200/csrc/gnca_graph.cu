@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_graph_bwd_gather(StepArgs a, const floa
 // ------------------------------------------------------------------------------------------------
 __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __restrict__ packed,
                            const float* __restrict__ rowsum, const float* __restrict__ gw_part, int nparts,
-                           float* __restrict__ grow, float* __restrict__ pw) {
+                           float* __restrict__ grow, float* __restrict__ pw, int stage) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, H = a.H, W = a.W, k = a.k;
   float* xbar = sm;              // [C]
@@ -174,15 +174,15 @@ __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __re
   float* gL = wv + k;            // [k]
   int* rlo = reinterpret_cast<int*>(gL + k);   // [k]
   int* rhi = rlo + k;                           // [k]
+  float* rss = reinterpret_cast<float*>(rhi + k);   // [C][H] when staged (see k_attn_weights)
   __shared__ float s_gtau;
   const float* rs = rowsum + (size_t)b * C * H;
   const float invHW = 1.0f / (float)(H * W);
   const bool torus = (a.flags & GNCA_F_TORUS) != 0;
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int c = tid; c < C; c += nt) {
-    float s = 0.f;
-    for (int y = 0; y < H; ++y) s += rs[c * H + y];
-    xbar[c] = s * invHW;
+  if (stage) {
+    for (int i = tid; i < C * H; i += nt) rss[i] = rs[i];
+    rs = rss;
   }
   for (int i = tid; i < k; i += nt) {
     int dy, dx;
@@ -190,6 +190,15 @@ __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __re
     int lo = 0, hi = H;
     if (!torus) { lo = max(0, -dy); hi = min(H, H - dy); }
     rlo[i] = lo; rhi[i] = max(lo, hi);
+    float gw = 0.f;               // dL/dw_i: the partials of the cell kernels, in order (one thread per offset)
+    for (int pidx = 0; pidx < nparts; ++pidx) gw += gw_part[((size_t)b * nparts + pidx) * GNCA_MAX_K + i];
+    gL[i] = gw;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += nt) {
+    float s = 0.f;
+    for (int y = 0; y < H; ++y) s += rs[c * H + y];
+    xbar[c] = s * invHW;
   }
   __syncthreads();
   for (int j = tid; j < d; j += nt) {
@@ -232,10 +241,7 @@ __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __re
     float dot = 0.f;
     for (int i = 0; i < k; ++i) {
       wv[i] /= se;
-      float gw = 0.f;
-      for (int pidx = 0; pidx < nparts; ++pidx) gw += gw_part[((size_t)b * nparts + pidx) * GNCA_MAX_K + i];
-      gL[i] = gw;                 // holds dL/dw_i for now
-      dot = fmaf(wv[i], gw, dot);
+      dot = fmaf(wv[i], gL[i], dot);          // gL holds dL/dw_i for now
     }
     float gtau = 0.f;
     for (int i = 0; i < k; ++i) {
@@ -288,7 +294,13 @@ __global__ void k_attn_param_reduce(int B, int C, int d, gnca_layout L, const fl
   const int n = 2 * d * C + 2 * d + 1;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += pw[(size_t)b * n + idx];
+    for (int b0 = 0; b0 < B; b0 += 8) {          // 8 loads in flight, added in sample order
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = b0 + q < B ? pw[(size_t)(b0 + q) * n + idx] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (b0 + q < B) s += v[q];
+    }
     int64_t dst;
     if (idx < d * C) dst = L.wq + idx;
     else if (idx < d * C + d) dst = L.bq + (idx - d * C);
@@ -330,10 +342,11 @@ size_t attn_bwd_scratch_bytes(const gnca_model& m, int B, int H, int nparts) {
 int run_attn_bwd(const gnca_model& m, const Packed& P, const float* packed, const StepArgs& a, const float* rowsum,
                  const AttnBwdScratch& sc, int nparts, float* gparams, cudaStream_t st) {
   const int C = m.C, d = m.d_model, k = a.k;
-  const size_t smem = (size_t)(4 * C + 2 * d + k * C + k * d + 3 * k) * 4 + 2 * k * 4 + 64;
+  const int stage = (size_t)C * a.H * 4 <= 32 * 1024;
+  const size_t smem = (size_t)(4 * C + 2 * d + k * C + k * d + 3 * k) * 4 + 2 * k * 4 + (stage ? (size_t)C * a.H * 4 : 0) + 64;
   if (smem > 48 * 1024)
     GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_attn_bwd<<<a.B, 128, smem, st>>>(a, P, C, d, packed, rowsum, sc.gw_part, nparts, sc.grow, sc.pw);
+  k_attn_bwd<<<a.B, 128, smem, st>>>(a, P, C, d, packed, rowsum, sc.gw_part, nparts, sc.grow, sc.pw, stage);
   GNCA_LAUNCH_CHECK();
   k_attn_param_reduce<<<4, 256, 0, st>>>(a.B, C, d, make_layout(m), sc.pw, gparams);
   GNCA_LAUNCH_CHECK();
