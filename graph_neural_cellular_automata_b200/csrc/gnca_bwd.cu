@@ -20,11 +20,11 @@ constexpr int kBThreads = 256;
 constexpr int kBChunk = 1024;
 constexpr int kBChunkSmall = 256;
 constexpr int kBTileW = 32, kBTileH = 8;
-constexpr int kMaxBwdBlocks = 148;
+constexpr int kMaxBwdBlocks = 296;      // two resident blocks per SM when the staged batch is 32 cells (C >= 16)
 
 template <int C>
 struct BwdCfg {
-  static constexpr int NB = (C <= 16) ? 64 : 32;   // active cells per staged batch
+  static constexpr int NB = (C < 16) ? 64 : 32;    // active cells per staged batch (32: two blocks fit an SM at C = 16)
   static constexpr int NBP = NB + 4;               // padded row stride (floats): conflict-free float4 rows
   static constexpr int TPC = kBThreads / NB;       // threads per cell in the cell-parallel phases
   static constexpr int CQ = C / TPC;               // channels per thread there
@@ -210,7 +210,7 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 }
 
 template <int C, int CH>
-__global__ void __launch_bounds__(kBThreads) k_bwd_mlp(BwdArgs A, Packed P, int hid, const float* __restrict__ packed) {
+__global__ void __launch_bounds__(kBThreads, 2) k_bwd_mlp(BwdArgs A, Packed P, int hid, const float* __restrict__ packed) {
   using K = BwdCfg<C>;
   constexpr int NB = K::NB, NBP = K::NBP, TPC = K::TPC, CQ = K::CQ, C3 = 3 * C;
   const StepArgs& a = A.s;
@@ -735,13 +735,25 @@ static int launch_step_bwd(const gnca_model& m, const Packed& P, const float* pa
   GNCA_LAUNCH_CHECK();
   const size_t smem = BwdSmem<C>::bytes(m.hidden, graph);
   if (smem > 226 * 1024) return GNCA_ERR_UNSUPPORTED;
+  // persistent blocks: as many as are resident at once (two per SM when the shared memory of a block allows it)
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    GNCA_CHECK_CUDA(cudaGetDevice(&dev));
+    GNCA_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int per_sm = 1;
   prof_begin(PROF_BWD_MLP, st);
   if (A.bchunk == kBChunkSmall) {
     GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_mlp<C, kBChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_bwd_mlp<C, kBChunkSmall><<<A.nblocks, kBThreads, smem, st>>>(A, P, m.hidden, packed);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bwd_mlp<C, kBChunkSmall>, kBThreads, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    const int nblk = min(A.n_items, min(kMaxBwdBlocks, per_sm * n_sm));
+    k_bwd_mlp<C, kBChunkSmall><<<nblk, kBThreads, smem, st>>>(A, P, m.hidden, packed);
   } else {
     GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_mlp<C, kBChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_bwd_mlp<C, kBChunk><<<A.nblocks, kBThreads, smem, st>>>(A, P, m.hidden, packed);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bwd_mlp<C, kBChunk>, kBThreads, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    const int nblk = min(A.n_items, min(kMaxBwdBlocks, per_sm * n_sm));
+    k_bwd_mlp<C, kBChunk><<<nblk, kBThreads, smem, st>>>(A, P, m.hidden, packed);
   }
   prof_end(PROF_BWD_MLP, st);
   GNCA_LAUNCH_CHECK();

@@ -116,11 +116,17 @@ __global__ void k_attn_weights(StepArgs a, Packed P, int C, int d, const float* 
   float* logit = KP + k * d;   // [k]
   int* rlo = reinterpret_cast<int*>(logit + k);   // [k]
   int* rhi = rlo + k;                              // [k]
-  float* rss = reinterpret_cast<float*>(rhi + k);  // [C][H] when staged
+  float* swq = reinterpret_cast<float*>(rhi + k);  // [d][C] query_proj / key_proj weights and biases (the dot-product
+  float* swk = swq + d * C;                        // loops below would otherwise chain L2 round trips)
+  float* sbq = swk + d * C;
+  float* sbk = sbq + d;
+  float* rss = sbk + d;                            // [C][H] when staged
   const float* rs = rowsum + (size_t)b * C * H;
   const float invHW = 1.0f / (float)(H * W);
   const bool torus = (a.flags & GNCA_F_TORUS) != 0;
   const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < d * C; i += nt) { swq[i] = packed[P.wq + i]; swk[i] = packed[P.wk + i]; }
+  for (int i = tid; i < d; i += nt) { sbq[i] = packed[P.bq + i]; sbk[i] = packed[P.bk + i]; }
   if (stage) {
     for (int i = tid; i < C * H; i += nt) rss[i] = rs[i];
     rs = rss;
@@ -147,14 +153,14 @@ __global__ void k_attn_weights(StepArgs a, Packed P, int C, int d, const float* 
   __syncthreads();
   for (int j = tid; j < d; j += nt) {
     float s = 0.f;
-    for (int c = 0; c < C; ++c) s = fmaf(packed[P.wq + j * C + c], xsum[c] * invHW, s);
-    qp[j] = s + packed[P.bq + j];
+    for (int c = 0; c < C; ++c) s = fmaf(swq[j * C + c], xsum[c] * invHW, s);
+    qp[j] = s + sbq[j];
   }
   for (int idx = tid; idx < k * d; idx += nt) {
     const int i = idx / d, j = idx - i * d;
     float s = 0.f;
-    for (int c = 0; c < C; ++c) s = fmaf(packed[P.wk + j * C + c], S[i * C + c], s);
-    KP[idx] = (s + (float)(rhi[i] - rlo[i]) * (float)W * packed[P.bk + j]) * invHW;
+    for (int c = 0; c < C; ++c) s = fmaf(swk[j * C + c], S[i * C + c], s);
+    KP[idx] = (s + (float)(rhi[i] - rlo[i]) * (float)W * sbk[j]) * invHW;
   }
   __syncthreads();
   for (int i = tid; i < k; i += nt) {
@@ -180,7 +186,7 @@ int run_attn_prepass(const gnca_model& m, const Packed& P, const float* packed, 
   k_rowsum<<<(rows + 7) / 8, 256, 0, st>>>(rows, a.W, a.x_in, ws.rowsum);
   GNCA_LAUNCH_CHECK();
   const int stage = (size_t)m.C * a.H * sizeof(float) <= 32 * 1024;
-  const size_t sm = (size_t)(m.C + m.d_model + a.k * (m.C + m.d_model) + 3 * a.k + 4 + (stage ? m.C * a.H : 0)) * sizeof(float);
+  const size_t sm = (size_t)(m.C + m.d_model + a.k * (m.C + m.d_model) + 3 * a.k + 4 + 2 * m.d_model * (m.C + 1) + (stage ? m.C * a.H : 0)) * sizeof(float);
   if (sm > 48 * 1024) GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_attn_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   k_attn_weights<<<a.B, 128, sm, st>>>(a, P, m.C, m.d_model, packed, ws.rowsum, ws.attn_w, stage);
   GNCA_LAUNCH_CHECK();

@@ -174,12 +174,18 @@ __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __re
   float* gL = wv + k;            // [k]
   int* rlo = reinterpret_cast<int*>(gL + k);   // [k]
   int* rhi = rlo + k;                           // [k]
-  float* rss = reinterpret_cast<float*>(rhi + k);   // [C][H] when staged (see k_attn_weights)
+  float* swq = reinterpret_cast<float*>(rhi + k);   // [d][C] weights / biases staged like the row sums (see k_attn_weights)
+  float* swk = swq + d * C;
+  float* sbq = swk + d * C;
+  float* sbk = sbq + d;
+  float* rss = sbk + d;                             // [C][H] when staged
   __shared__ float s_gtau;
   const float* rs = rowsum + (size_t)b * C * H;
   const float invHW = 1.0f / (float)(H * W);
   const bool torus = (a.flags & GNCA_F_TORUS) != 0;
   const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < d * C; i += nt) { swq[i] = packed[P.wq + i]; swk[i] = packed[P.wk + i]; }
+  for (int i = tid; i < d; i += nt) { sbq[i] = packed[P.bq + i]; sbk[i] = packed[P.bk + i]; }
   if (stage) {
     for (int i = tid; i < C * H; i += nt) rss[i] = rs[i];
     rs = rss;
@@ -203,8 +209,8 @@ __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __re
   __syncthreads();
   for (int j = tid; j < d; j += nt) {
     float s = 0.f;
-    for (int c = 0; c < C; ++c) s = fmaf(packed[P.wq + j * C + c], xbar[c], s);
-    qp[j] = s + packed[P.bq + j];
+    for (int c = 0; c < C; ++c) s = fmaf(swq[j * C + c], xbar[c], s);
+    qp[j] = s + sbq[j];
   }
   for (int idx = tid; idx < k * C; idx += nt) {
     const int i = idx / C, c = idx % C;
@@ -216,12 +222,12 @@ __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __re
   for (int idx = tid; idx < k * d; idx += nt) {
     const int i = idx / d, j = idx % d;
     float s = 0.f;
-    for (int c = 0; c < C; ++c) s = fmaf(packed[P.wk + j * C + c], S[i * C + c], s);
-    KP[idx] = (s + (float)(rhi[i] - rlo[i]) * (float)W * packed[P.bk + j]) * invHW;
+    for (int c = 0; c < C; ++c) s = fmaf(swk[j * C + c], S[i * C + c], s);
+    KP[idx] = (s + (float)(rhi[i] - rlo[i]) * (float)W * sbk[j]) * invHW;
   }
   for (int c = tid; c < C; c += nt) {
     float s = 0.f;
-    for (int j = 0; j < d; ++j) s = fmaf(packed[P.wk + j * C + c], qp[j], s);
+    for (int j = 0; j < d; ++j) s = fmaf(swk[j * C + c], qp[j], s);
     wkq[c] = s;
   }
   __syncthreads();
@@ -260,7 +266,7 @@ __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __re
   __syncthreads();
   for (int c = tid; c < C; c += nt) {
     float s = 0.f;
-    for (int j = 0; j < d; ++j) s = fmaf(packed[P.wq + j * C + c], gqp[j], s);
+    for (int j = 0; j < d; ++j) s = fmaf(swq[j * C + c], gqp[j], s);
     gxb[c] = s;
   }
   // per-sample parameter gradients: [wq d*C][bq d][wk d*C][bk d][scaling]
@@ -343,7 +349,7 @@ int run_attn_bwd(const gnca_model& m, const Packed& P, const float* packed, cons
                  const AttnBwdScratch& sc, int nparts, float* gparams, cudaStream_t st) {
   const int C = m.C, d = m.d_model, k = a.k;
   const int stage = (size_t)C * a.H * 4 <= 32 * 1024;
-  const size_t smem = (size_t)(4 * C + 2 * d + k * C + k * d + 3 * k) * 4 + 2 * k * 4 + (stage ? (size_t)C * a.H * 4 : 0) + 64;
+  const size_t smem = (size_t)(4 * C + 2 * d + k * C + k * d + 3 * k) * 4 + 2 * k * 4 + (size_t)2 * d * (C + 1) * 4 + (stage ? (size_t)C * a.H * 4 : 0) + 64;
   if (smem > 48 * 1024)
     GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_attn_bwd<<<a.B, 128, smem, st>>>(a, P, C, d, packed, rowsum, sc.gw_part, nparts, sc.grow, sc.pw, stage);
