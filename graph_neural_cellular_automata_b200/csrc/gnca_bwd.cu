@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bwd_mlp(BwdArgs A, Packed P, i
   int* scell = reinterpret_cast<int*>(slist + kBChunk);
   __shared__ int s_nact;
   __shared__ int swcount[kBThreads / 32], swbase[kBThreads / 32 + 1];
+  __shared__ int s_ody[GNCA_MAX_K], s_odx[GNCA_MAX_K];      // the step's sender offsets (reduced modulo the grid on a torus)
+  __shared__ float s_owt[GNCA_MAX_K];                        // and the sample's weights
 
   block_copy(sW1T, packed + P.w1t, C3 * hid);
   block_copy(sb1, packed + P.b1, pad4(hid));
@@ -277,6 +279,13 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bwd_mlp(BwdArgs A, Packed P, i
         cnt += __popc(bal[it]);
       }
       __syncthreads();   // previous item fully consumed slist / swbase
+      if (msg_on && threadIdx.x < a.k) {
+        int dy, dx;
+        step_offset(a, threadIdx.x, dy, dx);
+        s_ody[threadIdx.x] = torus ? dy % H : dy;
+        s_odx[threadIdx.x] = torus ? dx % W : 0;
+        s_owt[threadIdx.x] = a.attn_w ? __ldg(a.attn_w + (size_t)b * a.k + threadIdx.x) : 1.0f / (float)a.k;
+      }
       if (lane == 0) swcount[warp] = cnt;
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -308,24 +317,36 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bwd_mlp(BwdArgs A, Packed P, i
         int cell = 0, y = 0, x = 0;
         if (valid) { cell = cell0 + (int)slist[base + cell_l]; y = cell / W; x = cell - y * W; }
         if (part == 0 && cell_l < NB) scell[cell_l] = valid ? cell : -1;
+        // All loads of the phase are requested before the first use, without branches (the edge taps of the perception
+        // and of the senders' alive windows come from a clamped address; an idle lane reads cell 0 and drops it): the
+        // original per-channel / per-sender basic blocks paid ~2 k dependent L2 round trips per batch.
         const bool up = y > 0, dn = y < H - 1, lf = x > 0, rt = x < W - 1;
+        const int oU = up ? -W : 0, oD = dn ? W : 0, oL = lf ? -1 : 0, oR = rt ? 1 : 0;
+        float pv[CQ][9], gzv[CQ], uv[CQ];
+#pragma unroll
+        for (int cc = 0; cc < CQ; ++cc) {
+          const int c = part * CQ + cc;
+          const float* p = xs_base + (size_t)c * HW + cell;
+          pv[cc][0] = __ldg(p + (oU + oL)); pv[cc][1] = __ldg(p + oU); pv[cc][2] = __ldg(p + (oU + oR));
+          pv[cc][3] = __ldg(p + oL);        pv[cc][4] = __ldg(p);      pv[cc][5] = __ldg(p + oR);
+          pv[cc][6] = __ldg(p + (oD + oL)); pv[cc][7] = __ldg(p + oD); pv[cc][8] = __ldg(p + (oD + oR));
+          gzv[cc] = A.gz[((size_t)b * C + c) * HW + cell];
+          uv[cc] = gn ? A.u[((size_t)b * C + c) * HW + cell] : 0.f;
+        }
 #pragma unroll
         for (int cc = 0; cc < CQ; ++cc) {
           const int c = part * CQ + cc;
           float vid = 0.f, vsx = 0.f, vsy = 0.f, gd = 0.f;
           if (valid) {
-            const float* p = xs_base + (size_t)c * HW + cell;
-            const float a00 = (up && lf) ? __ldg(p - W - 1) : 0.f, a01 = up ? __ldg(p - W) : 0.f,
-                        a02 = (up && rt) ? __ldg(p - W + 1) : 0.f;
-            const float a10 = lf ? __ldg(p - 1) : 0.f, a12 = rt ? __ldg(p + 1) : 0.f;
-            const float a20 = (dn && lf) ? __ldg(p + W - 1) : 0.f, a21 = dn ? __ldg(p + W) : 0.f,
-                        a22 = (dn && rt) ? __ldg(p + W + 1) : 0.f;
-            vid = __ldg(p);
+            const float a00 = (up && lf) ? pv[cc][0] : 0.f, a01 = up ? pv[cc][1] : 0.f, a02 = (up && rt) ? pv[cc][2] : 0.f;
+            const float a10 = lf ? pv[cc][3] : 0.f, a12 = rt ? pv[cc][5] : 0.f;
+            const float a20 = (dn && lf) ? pv[cc][6] : 0.f, a21 = dn ? pv[cc][7] : 0.f, a22 = (dn && rt) ? pv[cc][8] : 0.f;
+            vid = pv[cc][4];
             vsx = (a00 - a02) + 2.f * (a10 - a12) + (a20 - a22);
             vsy = (a00 + 2.f * a01 + a02) - (a20 + 2.f * a21 + a22);
-            const float gz = A.gz[((size_t)b * C + c) * HW + cell];
+            const float gz = gzv[cc];
             if (gn) {
-              const float uh = (A.u[((size_t)b * C + c) * HW + cell] - mu) * rstd;
+              const float uh = (uv[cc] - mu) * rstd;
               gd = rstd * (gz * sgam[c] - s1n - uh * s2n);
             } else {
               gd = gz;
@@ -342,18 +363,55 @@ __global__ void __launch_bounds__(kBThreads, 2) k_bwd_mlp(BwdArgs A, Packed P, i
 #pragma unroll
           for (int cc = 0; cc < CQ; ++cc) xsv[cc] = 0.f;
           float as = 0.f;
-          if (valid) {
-            const float wuni = 1.0f / (float)a.k;
-            for (int i = 0; i < a.k; ++i) {
-              int dy, dx, qy, qx;
-              step_offset(a, i, dy, dx);
-              if (!sender_of(y, x, dy, dx, H, W, torus, qy, qx)) continue;
-              if (a2a && !alive_at(xs_base + 3 * HW, qy, qx, H, W, a.graph_alpha_thr)) continue;
-              const float w = a.attn_w ? __ldg(a.attn_w + (size_t)b * a.k + i) : wuni;
+          const float* alpha = xs_base + 3 * HW;
+          constexpr int SB = 4;                                  // senders per round
+#pragma unroll 1
+          for (int i0 = 0; i0 < a.k; i0 += SB) {
+            float w[SB], v[SB][CQ], al[SB][9];
+            int qy[SB], qx[SB];
+#pragma unroll
+            for (int sI = 0; sI < SB; ++sI) {
+              const int ii = min(i0 + sI, a.k - 1);
+              const int dy = s_ody[ii], dx = s_odx[ii];
+              int yy = y - dy, xx = torus ? x - dx : x;
+              bool ok = valid && i0 + sI < a.k;
+              if (torus) {
+                yy = yy < 0 ? yy + H : (yy >= H ? yy - H : yy);
+                xx = xx < 0 ? xx + W : (xx >= W ? xx - W : xx);
+              } else {
+                ok = ok && yy >= 0 && yy < H;
+                yy = ok ? yy : y;
+              }
+              qy[sI] = yy; qx[sI] = xx;
+              w[sI] = ok ? s_owt[ii] : 0.f;
+            }
+#pragma unroll
+            for (int sI = 0; sI < SB; ++sI) {
 #pragma unroll
               for (int cc = 0; cc < CQ; ++cc)
-                xsv[cc] = fmaf(w, __ldg(xs_base + (size_t)(part * CQ + cc) * HW + qy * W + qx), xsv[cc]);
-              as += w;
+                v[sI][cc] = __ldg(xs_base + (size_t)(part * CQ + cc) * HW + qy[sI] * W + qx[sI]);
+            }
+            if (a2a) {
+#pragma unroll
+              for (int sI = 0; sI < SB; ++sI) {
+                const int ru = (qy[sI] > 0 ? qy[sI] - 1 : qy[sI]) * W, rc = qy[sI] * W, rd = (qy[sI] < H - 1 ? qy[sI] + 1 : qy[sI]) * W;
+                const int xl = qx[sI] > 0 ? qx[sI] - 1 : qx[sI], xc = qx[sI], xr = qx[sI] < W - 1 ? qx[sI] + 1 : qx[sI];
+                al[sI][0] = __ldg(alpha + ru + xl); al[sI][1] = __ldg(alpha + ru + xc); al[sI][2] = __ldg(alpha + ru + xr);
+                al[sI][3] = __ldg(alpha + rc + xl); al[sI][4] = __ldg(alpha + rc + xc); al[sI][5] = __ldg(alpha + rc + xr);
+                al[sI][6] = __ldg(alpha + rd + xl); al[sI][7] = __ldg(alpha + rd + xc); al[sI][8] = __ldg(alpha + rd + xr);
+              }
+            }
+#pragma unroll
+            for (int sI = 0; sI < SB; ++sI) {
+              float ww = w[sI];
+              if (a2a) {
+                const float m = fmaxf(fmaxf(fmaxf(fmaxf(al[sI][0], al[sI][1]), fmaxf(al[sI][2], al[sI][3])),
+                                            fmaxf(fmaxf(al[sI][4], al[sI][5]), fmaxf(al[sI][6], al[sI][7]))), al[sI][8]);
+                ww = m > a.graph_alpha_thr ? ww : 0.f;
+              }
+#pragma unroll
+              for (int cc = 0; cc < CQ; ++cc) xsv[cc] = fmaf(ww, v[sI][cc], xsv[cc]);
+              as += ww;
             }
           }
 #pragma unroll

@@ -27,7 +27,6 @@ namespace gnca {
 
 constexpr int kRThreads = 512;
 constexpr int kRWarps = kRThreads / 32;
-constexpr int kRSlices = 8;      // hidden-dimension slices of layer 2 (partials reduced through smem)
 
 struct ResidentArgs {
   StepArgs s;                 // model scalars + schedule pointers (t / fire_u are set per step in-kernel)
@@ -131,8 +130,7 @@ __global__ void __launch_bounds__(kRThreads, 1) k_resident_fwd(ResidentArgs R, P
   float* AS = XSt + C * MBP;                            // [MBP]
   float* MSGt = AS + MBP;                               // [C][MBP]
   float* Ht = MSGt + C * MBP;                           // [hid][MBP]
-  float* RED = Ht + hid * MBP;                          // [kRSlices][C][MB]
-  float* Ut = RED + kRSlices * C * MB;                  // [C][nown] masked pre-norm update of active cells
+  float* Ut = Ht + hid * MBP;                           // [C][nown] masked pre-norm update of active cells
   int* s_q = reinterpret_cast<int*>(Ut + (size_t)C * nown);   // [MB][k] sender (lr*W+x) or -1
   int* s_actlist = s_q + MB * kk;                       // [nown] own-cell index of active cells (compacted)
   int* s_slot = s_actlist + nown;                       // [nown] slot in the active list or -1
@@ -637,7 +635,6 @@ static size_t resident_smem_bytes(int C, int hid, bool graph, int own, int halo,
   f += (size_t)pad4(C * plane_stride_of(own, halo, W));
   f += (size_t)pad4((own + 2) * W);
   f += (size_t)3 * C * MBP + (size_t)C * MBP + MBP + (size_t)C * MBP + (size_t)hid * MBP;
-  f += (size_t)kRSlices * C * MB;
   f += (size_t)C * own * W;
   size_t bytes = f * sizeof(float);
   bytes += (size_t)MB * (k > 0 ? k : 1) * sizeof(int) + 2 * (size_t)own * W * sizeof(int) + 2 * (size_t)own * W;
@@ -672,6 +669,7 @@ static int launch_resident(const gnca_model& m, const Packed& P, const float* pa
       int MB = 64;
       size_t smem = resident_smem_bytes(C, m.hidden, graph, own, halo, W, MB, R.s.k, R.T);
       if (smem > 226 * 1024) { MB = 32; smem = resident_smem_bytes(C, m.hidden, graph, own, halo, W, MB, R.s.k, R.T); }
+      if (smem > 226 * 1024) { MB = 16; smem = resident_smem_bytes(C, m.hidden, graph, own, halo, W, MB, R.s.k, R.T); }   // 40x40x32
       if (smem > 226 * 1024) continue;
       GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_resident_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cudaLaunchConfig_t q{};
