@@ -484,6 +484,9 @@ def run_trainer(args, world, rank, local_rank, dev, steps, warmup, regime="short
     for _ in range(warmup):
         tr.train_step(epoch=300)
     torch.cuda.synchronize()
+    import gc
+    gc.collect()
+    gc.freeze()          # as in the forward e2e loop: no full-heap collection on one of N ranks inside a timed all-reduce window
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank); sampler.start()
