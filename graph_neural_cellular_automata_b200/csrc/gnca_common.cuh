@@ -142,6 +142,7 @@ struct StepArgs {
   int npart;                          // GroupNorm partial slots per sample in `partials` (nchunks, or 3*nchunks: k_update_tc)
   const float* stats_ready;           // [B][2] (mean, rstd) already finished by the update path (k_update_tc2) or null
   const uint32_t* actbits;            // [B][ceil(HW/32)] active (alive & fire) bits of this step written by k_compact, or null
+  const uint32_t* alivebits;          // same layout: sender-alive bits (3x3 alpha max > graph_alpha_thr) of x_in, or null
   Offsets off;                        // host-supplied offsets (single step)
 };
 
@@ -191,7 +192,7 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t offset, 
 // ------------------------------------------------------------------------------------------------
 // alive: maxpool3x3(alpha) > thr with a -inf halo   (nca.py:55-62, ncagraph.py:85-92)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool alive_at(const float* __restrict__ alpha, int y, int x, int H, int W, float thr) {
+__device__ __forceinline__ float alive_max(const float* __restrict__ alpha, int y, int x, int H, int W) {
   float m = -INFINITY;
 #pragma unroll
   for (int i = -1; i <= 1; ++i) {
@@ -204,7 +205,10 @@ __device__ __forceinline__ bool alive_at(const float* __restrict__ alpha, int y,
       m = fmaxf(m, __ldg(alpha + yy * W + xx));
     }
   }
-  return m > thr;
+  return m;
+}
+__device__ __forceinline__ bool alive_at(const float* __restrict__ alpha, int y, int x, int H, int W, float thr) {
+  return alive_max(alpha, y, x, H, W) > thr;
 }
 
 // pre-gate updated alpha x~_3 = x_3 + gain * tanh(gn(u_3)) (ncagraph.py:153-155) with EXPLICIT roundings: the streaming

@@ -217,7 +217,8 @@ constexpr int kThreadsBal = 384;
 // halo instead of recomputing alive_at (nine alpha loads) and the Philox draw of every halo cell
 template <int CH>
 __global__ void __launch_bounds__(kThreads) k_compact(StepArgs a, int C, uint16_t* __restrict__ glist, int* __restrict__ cnt,
-                                                      uint32_t* __restrict__ actbits = nullptr) {
+                                                      uint32_t* __restrict__ actbits = nullptr,
+                                                      uint32_t* __restrict__ alivebits = nullptr) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int H = a.H, W = a.W, HW = H * W;
   __shared__ int swcount[kThreads / 32], swbase[kThreads / 32 + 1];
@@ -232,15 +233,21 @@ __global__ void __launch_bounds__(kThreads) k_compact(StepArgs a, int C, uint16_
 #pragma unroll
   for (int it = 0; it < kPerWarp / 32; ++it) {
     const int cell = cell0 + warp * kPerWarp + it * 32 + lane;
-    bool act = false;
+    bool act = false, sal = false;
     if (cell < HW) {
       const int y = cell / W, x = cell - y * W;
-      act = alive_at(alpha, y, x, H, W, a.alpha_thr) && fires(a, fr, b, cell);
+      const float mx = alive_max(alpha, y, x, H, W);          // one window maximum serves both thresholds
+      act = mx > a.alpha_thr && fires(a, fr, b, cell);
+      sal = mx > a.graph_alpha_thr;
     }
     bal[it] = __ballot_sync(0xffffffffu, act);
     n += __popc(bal[it]);
-    if (actbits && lane == 0 && cell0 + warp * kPerWarp + it * 32 < HW)
-      actbits[(size_t)b * ((HW + 31) >> 5) + ((cell0 + warp * kPerWarp + it * 32) >> 5)] = bal[it];
+    const size_t word = (size_t)b * ((HW + 31) >> 5) + ((cell0 + warp * kPerWarp + it * 32) >> 5);
+    if (actbits && lane == 0 && cell0 + warp * kPerWarp + it * 32 < HW) actbits[word] = bal[it];
+    if (alivebits) {        // the step's sender-alive bits: k_update_tc tests one bit instead of nine alpha loads per sender
+      const uint32_t sb = __ballot_sync(0xffffffffu, sal);
+      if (lane == 0 && cell0 + warp * kPerWarp + it * 32 < HW) alivebits[word] = sb;
+    }
   }
   if (lane == 0) swcount[warp] = n;
   __syncthreads();
@@ -656,6 +663,7 @@ FwdWorkspace carve_fwd_workspace(void* base, const gnca_model& m, int B, int H, 
   ws.absmean = reinterpret_cast<float*>(p + o); o = align_up(o + (size_t)B * H * W * sizeof(float), 256);
   ws.tc2 = p + o; o = align_up(o + update_tc2_workspace_bytes(B, H, W), 256);
   ws.actbits = reinterpret_cast<uint32_t*>(p + o); o = align_up(o + (size_t)B * ((H * W + 31) / 32) * sizeof(uint32_t), 256);
+  ws.alivebits = reinterpret_cast<uint32_t*>(p + o); o = align_up(o + (size_t)B * ((H * W + 31) / 32) * sizeof(uint32_t), 256);
   ws.bytes = o;
   return ws;
 }
@@ -682,6 +690,7 @@ static int launch_update(const gnca_model& m, const Packed& P, const float* pack
   dim3 g1(a.nchunks, a.B);
   a.stats_ready = nullptr;
   a.actbits = nullptr;
+  a.alivebits = nullptr;
   if (a.chunk == kChunkSmall) {
     a.npart = a.nchunks;
     GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_update<C, kChunkSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -708,8 +717,10 @@ static int launch_update(const gnca_model& m, const Packed& P, const float* pack
     int* cnt = reinterpret_cast<int*>(reinterpret_cast<char*>(ws.partials) + used);
     int* prefix = cnt + (size_t)a.B * a.nchunks;
     uint16_t* glist = reinterpret_cast<uint16_t*>(ws.absmean);
-    k_compact<kChunk><<<g1, kThreads, 0, st>>>(a, C, glist, cnt, ws.actbits);
+    const bool want_alive = use_tc && graph && (a.flags & GNCA_F_ALIVE_TO_ALIVE) && a.k > 0 && !getenv("GNCA_NO_ALIVEBITS");
+    k_compact<kChunk><<<g1, kThreads, 0, st>>>(a, C, glist, cnt, ws.actbits, want_alive ? ws.alivebits : nullptr);
     a.actbits = ws.actbits;
+    a.alivebits = want_alive ? ws.alivebits : nullptr;
     k_scan<<<a.B, 32, 0, st>>>(a.nchunks, cnt, prefix);
     if (use_tc) {
       g_launches += 2;

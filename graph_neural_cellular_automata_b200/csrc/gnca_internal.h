@@ -12,6 +12,7 @@ struct FwdWorkspace {
   float* absmean;     // [B][H][W]
   void* tc2;          // tile masks / lists / partials of k_update_tc2 (update_tc2_workspace_bytes)
   uint32_t* actbits;  // [B][ceil(HW/32)] active bits of the step (k_compact -> k_apply)
+  uint32_t* alivebits;   // [B][ceil(HW/32)] sender-alive bits of the step (k_compact -> k_update_tc)
   size_t bytes;
 };
 

@@ -81,12 +81,13 @@ __device__ __forceinline__ void perceive_batched(const float* __restrict__ xs, i
 // is anything consumed.  A sender that is out of range or not alive contributes with weight 0 (fmaf(0, finite, acc) ==
 // acc: the bits of the generic function's `continue`).
 template <int C>
-__device__ __forceinline__ void gather_senders_pairs(const StepArgs& a, const float* __restrict__ xs_base, int y, int x,
+__device__ __forceinline__ void gather_senders_pairs(const StepArgs& a, const float* __restrict__ xs_base, int b, int y, int x,
                                                      const int* __restrict__ s_dy, const int* __restrict__ s_dx,
                                                      const float* __restrict__ s_wt, float (&xs)[C], float& as) {
   const int H = a.H, W = a.W, HW = H * W, k = a.k;
   const bool torus = (a.flags & GNCA_F_TORUS) != 0, A2A = (a.flags & GNCA_F_ALIVE_TO_ALIVE) != 0;
   const float* __restrict__ alpha = xs_base + 3 * HW;
+  const uint32_t* __restrict__ abits = a.alivebits ? a.alivebits + (size_t)b * ((HW + 31) >> 5) : nullptr;
 #pragma unroll
   for (int c = 0; c < C; ++c) xs[c] = 0.f;
   as = 0.f;
@@ -116,14 +117,23 @@ __device__ __forceinline__ void gather_senders_pairs(const StepArgs& a, const fl
 #pragma unroll
       for (int c = 0; c < C; ++c) v[s][c] = __ldg(qp + (size_t)c * HW);
     }
+    uint32_t abit[2] = {0u, 0u};
     if (A2A) {
+      if (a.alivebits) {            // k_compact left the sender-alive bit of every cell of x_in: one word instead of nine taps
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int ru = (qy[s] > 0 ? qy[s] - 1 : qy[s]) * W, rc = qy[s] * W, rd = (qy[s] < H - 1 ? qy[s] + 1 : qy[s]) * W;
-        const int xl = qx[s] > 0 ? qx[s] - 1 : qx[s], xc = qx[s], xr = qx[s] < W - 1 ? qx[s] + 1 : qx[s];
-        al[s][0] = __ldg(alpha + ru + xl); al[s][1] = __ldg(alpha + ru + xc); al[s][2] = __ldg(alpha + ru + xr);
-        al[s][3] = __ldg(alpha + rc + xl); al[s][4] = __ldg(alpha + rc + xc); al[s][5] = __ldg(alpha + rc + xr);
-        al[s][6] = __ldg(alpha + rd + xl); al[s][7] = __ldg(alpha + rd + xc); al[s][8] = __ldg(alpha + rd + xr);
+        for (int s = 0; s < 2; ++s) {
+          const int q = qy[s] * W + qx[s];
+          abit[s] = (__ldg(abits + (q >> 5)) >> (q & 31)) & 1u;
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int ru = (qy[s] > 0 ? qy[s] - 1 : qy[s]) * W, rc = qy[s] * W, rd = (qy[s] < H - 1 ? qy[s] + 1 : qy[s]) * W;
+          const int xl = qx[s] > 0 ? qx[s] - 1 : qx[s], xc = qx[s], xr = qx[s] < W - 1 ? qx[s] + 1 : qx[s];
+          al[s][0] = __ldg(alpha + ru + xl); al[s][1] = __ldg(alpha + ru + xc); al[s][2] = __ldg(alpha + ru + xr);
+          al[s][3] = __ldg(alpha + rc + xl); al[s][4] = __ldg(alpha + rc + xc); al[s][5] = __ldg(alpha + rc + xr);
+          al[s][6] = __ldg(alpha + rd + xl); al[s][7] = __ldg(alpha + rd + xc); al[s][8] = __ldg(alpha + rd + xr);
+        }
       }
     }
 #pragma unroll
@@ -132,7 +142,7 @@ __device__ __forceinline__ void gather_senders_pairs(const StepArgs& a, const fl
       if (A2A) {
         const float m = fmaxf(fmaxf(fmaxf(fmaxf(al[s][0], al[s][1]), fmaxf(al[s][2], al[s][3])),
                                     fmaxf(fmaxf(al[s][4], al[s][5]), fmaxf(al[s][6], al[s][7]))), al[s][8]);
-        ww = m > a.graph_alpha_thr ? ww : 0.f;
+        ww = (a.alivebits ? abit[s] != 0u : m > a.graph_alpha_thr) ? ww : 0.f;
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) xs[c] = fmaf(ww, v[s][c], xs[c]);
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_update_tc(StepArgs a, Packed 
       if (do_msg) {
         if (cell >= 0) {
           float xsnd[C], as;
-          gather_senders_pairs<C>(a, xs_base, cy, cx, s_dy, s_dx, s_wt, xsnd, as);
+          gather_senders_pairs<C>(a, xs_base, b, cy, cx, s_dy, s_dx, s_wt, xsnd, as);
           // agg = Wm xs + bm as (msg_proj by linearity), message = gain * tanh(agg) on the updated channels
           // (ncagraph.py:94-104,141): a rolled loop over quads of output channels keeps the kernel's code inside the
           // instruction cache
