@@ -105,3 +105,34 @@ def test_rollout_properties_at_scale():
     assert torch.equal(whole, two)
     # (5) the state stays finite and alive
     assert torch.isfinite(whole).all() and float((whole[:, 3] > 0.1).float().mean()) > 0.01
+
+
+@pytest.mark.parametrize("Hh,Ww,B", [(64, 64, 80), (48, 66, 80), (40, 75, 100)])
+@pytest.mark.parametrize("kernel", ["tc", "ffma"])
+def test_large_problem_path_at_the_grid_edges(Hh, Ww, B, kernel, monkeypatch):
+    """The blobs of the tests above never touch the border.  Here the whole grid is alive except a dead band in the
+    middle: every edge / corner cell runs the zero-halo perception (clamped taps + selects; the 8-byte tap pairs when W is
+    even, the scalar taps at W = 75) and the torus wrap of the sender gather in the large-problem kernels."""
+    monkeypatch.delenv("GNCA_TC_V2", raising=False); monkeypatch.delenv("GNCA_NO_TC", raising=False)
+    if kernel == "ffma":
+        monkeypatch.setenv("GNCA_NO_TC", "1")
+    torch.manual_seed(9); random.seed(9)
+    m = G.NeuralCAGraph(C, update_hidden=HID, img_size=Hh, update_gain=0.1, alpha_thr=0.1, message_gain=0.3,
+                        hidden_only=True, graph_zero_padded_shift=False)
+    with torch.no_grad():
+        m.update_net[2].weight.normal_(0, 0.05)
+        m.norm.weight.uniform_(0.5, 1.5); m.norm.bias.normal_(0, 0.1)
+    p = {k: v.detach().double() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    x = torch.rand(B, C, Hh, Ww)
+    x[:, :, Hh // 2 - 4:Hh // 2 + 4, 5:Ww - 5] = 0.0                  # a dead band, not touching the border
+    x[::3, 3] *= (torch.rand((B + 2) // 3, Hh, Ww) > 0.3).float()       # ragged alive sets on every third sample
+    fu = torch.rand(B, 1, Hh, Ww)
+    chosen = [(4, -4), (-4, 4), (0, 3), (-3, 0), (1, 1), (-2, 4), (4, 0), (0, -4)]       # wraps on every side
+    cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=True, message_gain=0.3, hidden_only=True,
+                       zero_padded_shift=False)
+    ref = O.nca_step(x.double(), p, cfg, 0.5, fu.double(), chosen)
+    with torch.no_grad():
+        out = m.step(x.to(DEV), 0.5, fire_u=fu.to(DEV), chosen=chosen)
+    assert max_rel(out.cpu(), ref) < 1e-5, max_rel(out.cpu(), ref)
+    assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))
