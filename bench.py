@@ -345,6 +345,9 @@ def run_workload(cfg, args, world, rank, local_rank, dev, steps, warmup, with_ro
     for i in range(warmup):
         one_rollout(x0_dev, scheds[i])
     torch.cuda.synchronize()
+    import gc
+    gc.collect()
+    gc.freeze()          # no full-heap Python collection on one of N ranks inside the timed region (max over ranks is reported)
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
