@@ -136,3 +136,34 @@ def test_large_problem_path_at_the_grid_edges(Hh, Ww, B, kernel, monkeypatch):
         out = m.step(x.to(DEV), 0.5, fire_u=fu.to(DEV), chosen=chosen)
     assert max_rel(out.cpu(), ref) < 1e-5, max_rel(out.cpu(), ref)
     assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))
+
+
+@pytest.mark.parametrize("flags", [dict(hidden_only=False), dict(graph_alive_to_alive=False), dict(use_groupnorm=False),
+                                   dict(hidden_only=False, graph_alive_to_alive=False, use_groupnorm=False)])
+@pytest.mark.parametrize("Cc", [16, 32])
+def test_tensor_core_path_constructor_flags(flags, Cc):
+    """The non-default constructor flags (compiled into every kernel, exercised only at 40x40) on the
+    tensor-core large-problem path, C = 16 and 32: one step against the fp64 oracle."""
+    torch.manual_seed(13); random.seed(13)
+    Hh, B = 64, 80
+    m = G.NeuralCAGraph(Cc, update_hidden=HID, img_size=Hh, update_gain=0.1, alpha_thr=0.1, message_gain=0.3,
+                        graph_zero_padded_shift=False, **{"hidden_only": True, **flags})
+    with torch.no_grad():
+        m.update_net[2].weight.normal_(0, 0.05)
+        if flags.get("use_groupnorm", True):
+            m.norm.weight.uniform_(0.5, 1.5); m.norm.bias.normal_(0, 0.1)
+    p = {k: v.detach().double() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    yy, xx = torch.meshgrid(torch.arange(Hh), torch.arange(Hh), indexing="ij")
+    x = torch.rand(B, Cc, Hh, Hh) * (((yy - 30) ** 2 + (xx - 35) ** 2) < 24 ** 2).float()
+    x[1::2, 3] *= (torch.rand(B // 2, Hh, Hh) > 0.4).float()
+    fu = torch.rand(B, 1, Hh, Hh)
+    chosen = random.sample(m.graph.offsets, 8)
+    cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=True, message_gain=0.3, zero_padded_shift=False,
+                       hidden_only=flags.get("hidden_only", True), alive_to_alive=flags.get("graph_alive_to_alive", True),
+                       use_groupnorm=flags.get("use_groupnorm", True))
+    ref = O.nca_step(x.double(), p, cfg, 0.5, fu.double(), chosen)
+    with torch.no_grad():
+        out = m.step(x.to(DEV), 0.5, fire_u=fu.to(DEV), chosen=chosen)
+    assert max_rel(out.cpu(), ref) < 1e-5, max_rel(out.cpu(), ref)
+    assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))
