@@ -167,3 +167,33 @@ def test_tensor_core_path_constructor_flags(flags, Cc):
         out = m.step(x.to(DEV), 0.5, fire_u=fu.to(DEV), chosen=chosen)
     assert max_rel(out.cpu(), ref) < 1e-5, max_rel(out.cpu(), ref)
     assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))
+
+
+def test_tensor_core_rollout_vs_oracle():
+    """Four steps on the tensor-core large-problem path (64x64x32, B = 80) against the fp64 oracle fed the same uniforms and
+    offsets: the per-step hand-over k_compact (lists, active bits, sender-alive bits) -> k_update_tc -> k_apply."""
+    torch.manual_seed(17); random.seed(17)
+    Hh, B, T = 64, 80, 4
+    m = G.NeuralCAGraph(C, update_hidden=HID, img_size=Hh, update_gain=0.1, alpha_thr=0.1, message_gain=0.3,
+                        hidden_only=True, graph_zero_padded_shift=False)
+    with torch.no_grad():
+        m.update_net[2].weight.normal_(0, 0.05)
+        m.norm.weight.uniform_(0.5, 1.5); m.norm.bias.normal_(0, 0.1)
+    p = {k: v.detach().double() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    yy, xx = torch.meshgrid(torch.arange(Hh), torch.arange(Hh), indexing="ij")
+    x0 = torch.rand(B, C, Hh, Hh) * (((yy - 30) ** 2 + (xx - 35) ** 2) < 26 ** 2).float()
+    x0[::2, 3] *= (torch.rand(B // 2, Hh, Hh) > 0.5).float()
+    fu = torch.rand(T, B, Hh, Hh)
+    chosen = [random.sample(m.graph.offsets, 8) for _ in range(T)]
+    gains = [0.3, 0.0, 0.3, 0.3]
+    sched = make_schedule(m, B, Hh, Hh, T, fire_rate=0.5, fire_u=fu.to(DEV), offsets=chosen, message_gains=gains)
+    with torch.no_grad():
+        out = rollout(m, x0.to(DEV), sched, impl="streaming")
+    ref = x0.double()
+    for t in range(T):
+        cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=True, message_gain=gains[t], hidden_only=True,
+                           zero_padded_shift=False)
+        ref = O.nca_step(ref, p, cfg, 0.5, fu[t].unsqueeze(1).double(), chosen[t])
+    assert rel_err(out.cpu(), ref.float()) < 1e-5, rel_err(out.cpu(), ref.float())
+    assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))
