@@ -228,3 +228,50 @@ def test_classic_model_on_the_tensor_core_path(C, Hh, B):
         out = m.step(x.to(DEV), 0.5, fire_u=fu.to(DEV))
     assert max_rel(out.cpu(), ref) < 1e-5, max_rel(out.cpu(), ref)
     assert torch.equal(GF.alive_mask(out, 0.1).cpu(), O.alive_mask(ref.float(), 0.1))
+
+
+@pytest.mark.parametrize("torus", [True, False])
+@pytest.mark.parametrize("Cc", [8, 32])
+def test_streaming_backward_other_channel_counts_vs_oracle_autograd(Cc, torus):
+    """The streaming backward at C != 16 (32-cell staged batches with 4 channels per thread at C = 32, 64-cell batches at
+    C = 8), torus and zero-padded shift (the attention-weight gradient path): a 3-step rollout's gradients against torch
+    autograd through the fp64 oracle fed the same uniforms and offsets."""
+    import random
+    torch.manual_seed(21); random.seed(21)
+    Hh, Ww, B, T = 24, 28, 3, 3
+    m = G.NeuralCAGraph(Cc, update_hidden=128, img_size=Hh, update_gain=0.1, alpha_thr=0.1, message_gain=0.3,
+                        hidden_only=True, graph_zero_padded_shift=not torus)
+    with torch.no_grad():
+        m.update_net[2].weight.normal_(0, 0.05)
+        m.norm.weight.uniform_(0.5, 1.5); m.norm.bias.normal_(0, 0.1)
+    p = {k: v.detach().double().requires_grad_(v.is_floating_point() and "perception" not in k) for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    yy, xx = torch.meshgrid(torch.arange(Hh), torch.arange(Ww), indexing="ij")
+    x0 = torch.rand(B, Cc, Hh, Ww) * (((yy - 11) ** 2 + (xx - 13) ** 2) < 81).float()
+    fu = torch.rand(T, B, Hh, Ww)
+    chosen = [random.sample(m.graph.offsets, 8) for _ in range(T)]
+    loss_of = lambda xT: (xT[:, :4] ** 2).mean() + 0.1 * xT[:, 4:].mean()
+    # oracle, fp64, autograd
+    xr = x0.double().requires_grad_(True)
+    ref = xr
+    for t in range(T):
+        cfg = O.StepConfig(update_gain=0.1, alpha_thr=0.1, graph=True, message_gain=0.3, hidden_only=True,
+                           zero_padded_shift=not torus)
+        ref = O.nca_step(ref, p, cfg, 0.6, fu[t].unsqueeze(1).double(), chosen[t])
+    loss_of(ref).backward()
+    # library, streaming kernels
+    from graph_neural_cellular_automata_b200.rollout import make_schedule, rollout
+    for q in m.parameters():
+        q.grad = None
+    xg = x0.to(DEV).requires_grad_(True)
+    sched = make_schedule(m, B, Hh, Ww, T, fire_rate=0.6, fire_u=fu.to(DEV), offsets=chosen)
+    out = rollout(m, xg, sched, impl="streaming")
+    loss_of(out).backward()
+    assert rel_err(out.detach().cpu(), ref.detach().float()) < 1e-5
+    assert rel_err(xg.grad.cpu(), xr.grad.float()) < 1e-4, rel_err(xg.grad.cpu(), xr.grad.float())
+    for n, q in m.named_parameters():
+        gr = p[n].grad
+        if gr is None or float(gr.abs().max()) < 1e-12:          # torus: the softmax weights are uniform, fp64 noise ~1e-23
+            assert q.grad is None or float(q.grad.abs().max()) <= 1e-7, n
+            continue
+        assert rel_err(q.grad.cpu(), gr.float()) < 1e-4, (n, rel_err(q.grad.cpu(), gr.float()))
