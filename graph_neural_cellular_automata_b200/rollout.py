@@ -197,6 +197,13 @@ class History:
         return self.x[i]
 
 
+_QUANT_SLACK_BYTES = 8 << 30        # never over-allocate more than this for the sake of a stable block size
+
+
+def _round_up_steps(T: int, q: int = 64) -> int:
+    return T if T <= 16 else -(-T // q) * q
+
+
 BPTT_MAX_BYTES = 48 << 30      # above this the record buffer is not worth it: dense history + streaming backward
 
 
@@ -217,6 +224,12 @@ def rollout_fwd_raw(desc, packed, x0: torch.Tensor, sched: Schedule, *, history:
     if history and impl in (0, 2) and T > 0:
         nb = lib.gnca_bptt_bytes(C.byref(desc), B, H, W, T)
         if 0 < nb <= BPTT_MAX_BYTES:
+            # the record buffer is GBs (T*B*H*W*1.4 KB worst case): sized for T rounded up to 64 steps, so that rollouts of
+            # slightly different lengths (per-iteration step counts of the trainer) ask the caching allocator for the SAME
+            # block instead of a fresh cudaMalloc whenever a new maximum shows up (70 ms for 29 GB in the long regime)
+            nb_q = lib.gnca_bptt_bytes(C.byref(desc), B, H, W, _round_up_steps(T))
+            if nb <= nb_q <= BPTT_MAX_BYTES and nb_q - nb <= _QUANT_SLACK_BYTES:
+                nb = nb_q
             bptt = torch.empty(nb, dtype=torch.uint8, device=x0.device)
             hist = torch.empty(T + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device) if keep_x else None
             rc = lib.gnca_rollout_fwd_bptt(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(x0), GF._ptr(xT),
@@ -226,10 +239,13 @@ def rollout_fwd_raw(desc, packed, x0: torch.Tensor, sched: Schedule, *, history:
                 return xT, History(hist, bptt=bptt, shape=(T + 1, B, Cc, H, W))
     hist = uh = sh = None
     if history:
-        hist = torch.empty(T + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device)
+        Tq = _round_up_steps(T)              # same quantised allocation for the dense history (prefix views)
+        if (Tq - T) * B * Cc * H * W * 4 > _QUANT_SLACK_BYTES:
+            Tq = T
+        hist = torch.empty(Tq + 1, B, Cc, H, W, dtype=torch.float32, device=x0.device)[:T + 1]
         if keep_u and T > 0:
-            uh = torch.empty(T, B, Cc, H, W, dtype=torch.float32, device=x0.device)
-            sh = torch.empty(T, B, 2, dtype=torch.float32, device=x0.device)
+            uh = torch.empty(Tq, B, Cc, H, W, dtype=torch.float32, device=x0.device)[:T]
+            sh = torch.empty(Tq, B, 2, dtype=torch.float32, device=x0.device)[:T]
     _lib.check(lib.gnca_rollout_fwd(C.byref(desc), GF._ptr(packed), B, H, W, C.byref(cs), GF._ptr(x0), GF._ptr(xT),
                                     GF._ptr(hist), GF._ptr(sh), GF._ptr(uh), GF._ptr(ws), ws.numel(), int(impl),
                                     GF._stream()), "gnca_rollout_fwd")

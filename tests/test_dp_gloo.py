@@ -2,6 +2,7 @@
 gradient, the all-gather of per-sample losses and the bit-exact global worst-k indices."""
 import os
 import socket
+import tempfile
 
 import torch
 import torch.distributed as dist
@@ -27,18 +28,17 @@ def _worker(rank, world, port, out):
     per = sh.allgather(sh.take(per_global_truth).contiguous())
     worst = worst_k_indices(per, 0.25)
     states = sh.allgather(sh.take(torch.arange(B * 6, dtype=torch.float32).view(B, 2, 3)).contiguous())
-    out[rank] = (g, per, worst, states, grads_per_sample.sum(0), per_global_truth)
+    torch.save((g, per, worst, states, grads_per_sample.sum(0), per_global_truth), os.path.join(out, f"{rank}.pt"))   # files, not a forked Manager
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_dp_two_ranks_gloo():
     world = 2
-    mgr = mp.Manager()
-    out = mgr.dict()
+    out = tempfile.mkdtemp(prefix="gnca_dp_")
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
-    g0, per0, w0, st0, gsum, truth = out[0]
-    g1, per1, w1, st1, _, _ = out[1]
+    g0, per0, w0, st0, gsum, truth = torch.load(os.path.join(out, "0.pt"))
+    g1, per1, w1, st1, _, _ = torch.load(os.path.join(out, "1.pt"))
     assert torch.equal(g0, g1)                                        # identical on every rank
     assert torch.allclose(g0, gsum, rtol=1e-6, atol=1e-6)            # == single-process sum over the batch
     assert torch.equal(per0, truth) and torch.equal(per1, truth)

@@ -7,6 +7,7 @@ draws the global batch's uniforms from the same seeded stream and takes its slic
 import os
 import random
 import socket
+import tempfile
 
 import numpy as np
 import pytest
@@ -47,18 +48,23 @@ def _run(rank, world, port, out, sharding="replicated"):
         o = tr.train_step(epoch=150)
         rec.append({"per": o["per_sample"].cpu(), "worst": o["worst"].cpu(), "gflat": o["gflat"].cpu(), "steps": o["steps"].copy()})
     torch.cuda.synchronize()
-    out[(world, rank, sharding)] = {"rec": rec, "flat": tr.opt.flat.cpu(), "pool": tr.pool.pool.cpu()}
+    # results go through files: a multiprocessing.Manager would FORK a server out of the (multi-threaded, CUDA-initialised)
+    # pytest process, and that server aborted once inside a garbage collection
+    torch.save({"rec": rec, "flat": tr.opt.flat.cpu(), "pool": tr.pool.pool.cpu()}, os.path.join(out, f"{world}_{rank}_{sharding}.pt"))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _load(out, world, rank, sharding):
+    return torch.load(os.path.join(out, f"{world}_{rank}_{sharding}.pt"), weights_only=False)
+
+
 def test_two_ranks_equal_one_rank():
-    mgr = mp.Manager()
-    out = mgr.dict()
+    out = tempfile.mkdtemp(prefix="gnca_dp_")
     mp.spawn(_run, args=(1, 0, out), nprocs=1, join=True)
     mp.spawn(_run, args=(2, _free_port(), out), nprocs=2, join=True)
-    one, r0, r1 = out[(1, 0, "replicated")], out[(2, 0, "replicated")], out[(2, 1, "replicated")]
+    one, r0, r1 = _load(out, 1, 0, "replicated"), _load(out, 2, 0, "replicated"), _load(out, 2, 1, "replicated")
     for it in range(2):
         a, b, c = one["rec"][it], r0["rec"][it], r1["rec"][it]
         assert np.array_equal(a["steps"], b["steps"]) and np.array_equal(a["steps"], c["steps"])     # same host RNG replay
@@ -75,10 +81,9 @@ def test_owner_sharded_pool_two_ranks():
     """pool_sharding="owner" (rank r owns pool_size / world slots, no state all-gather): both ranks agree on the
     all-reduced gradient, the global per-sample losses, the worst-k indices and the parameters; each rank's pool shard has
     pool_size / world slots, changed only in the slots it drew, with its members of the global worst-k set reseeded."""
-    mgr = mp.Manager()
-    out = mgr.dict()
+    out = tempfile.mkdtemp(prefix="gnca_dp_")
     mp.spawn(_run, args=(2, _free_port(), out, "owner"), nprocs=2, join=True)
-    r0, r1 = out[(2, 0, "owner")], out[(2, 1, "owner")]
+    r0, r1 = _load(out, 2, 0, "owner"), _load(out, 2, 1, "owner")
     assert r0["pool"].shape[0] == 16 and r1["pool"].shape[0] == 16
     for it in range(2):
         b, c = r0["rec"][it], r1["rec"][it]
