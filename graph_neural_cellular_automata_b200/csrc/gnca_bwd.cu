@@ -824,7 +824,7 @@ static int launch_step_bwd(const gnca_model& m, const Packed& P, const float* pa
   prof_end(PROF_BWD_MLP, st);
   GNCA_LAUNCH_CHECK();
   if (A.gw_part) {
-    int rc = run_attn_bwd(m, P, packed, a, A.zp_rowsum, A.zp_scratch, A.nchunks, gparams, st);
+    int rc = run_attn_bwd(m, P, packed, a, A.zp_rowsum, A.zp_scratch, A.nchunks, gparams, st, /*defer_reduce=*/true);
     if (rc) return rc;
   }
   dim3 g3((a.H * a.W + 255) / 256, a.B);
@@ -857,6 +857,10 @@ int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, cons
     int rc = run_attn_prepass(m, P, packed, a, fws, st);
     if (rc) return rc;
     GNCA_CHECK_CUDA(cudaMemsetAsync(w.attn.gw_part, 0, w.gw_bytes, st));
+    // per-sample gradients of query_proj / key_proj / scaling: summed over the steps of a BPTT in place, reduced over the
+    // samples once after its last step (zero_partials / reduce_partials bracket the steps)
+    if (zero_partials)
+      GNCA_CHECK_CUDA(cudaMemsetAsync(w.attn.pw, 0, (size_t)a.B * (2 * m.d_model * m.C + 2 * m.d_model + 1) * sizeof(float), st));
   }
   BwdArgs A{};
   A.s = a;
@@ -880,6 +884,7 @@ int run_step_bwd(const gnca_model& m, const Packed& P, const float* packed, cons
   if (reduce_partials) {
     k_bwd_reduce<<<(int)((A.wtotal + 255) / 256), 256, 0, st>>>(kMaxBwdBlocks, A.wtotal, w.wpart, gparams);
     GNCA_LAUNCH_CHECK();
+    if (zp) { rc = run_attn_param_reduce(m, a.B, w.attn, gparams, st); if (rc) return rc; }
   }
   return 0;
 }

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_graph_bwd_gather(StepArgs a, const floa
 // ------------------------------------------------------------------------------------------------
 __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __restrict__ packed,
                            const float* __restrict__ rowsum, const float* __restrict__ gw_part, int nparts,
-                           float* __restrict__ grow, float* __restrict__ pw, int stage) {
+                           float* __restrict__ grow, float* __restrict__ pw, int stage, int accumulate) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, H = a.H, W = a.W, k = a.k;
   float* xbar = sm;              // [C]
@@ -269,22 +269,24 @@ __global__ void k_attn_bwd(StepArgs a, Packed P, int C, int d, const float* __re
     for (int j = 0; j < d; ++j) s = fmaf(swq[j * C + c], gqp[j], s);
     gxb[c] = s;
   }
-  // per-sample parameter gradients: [wq d*C][bq d][wk d*C][bk d][scaling]
+  // per-sample parameter gradients: [wq d*C][bq d][wk d*C][bk d][scaling]; `accumulate`: added to the slot (a BPTT sums the
+  // steps here and reduces over the samples once at the end) instead of overwriting it
   float* pwb = pw + (size_t)b * (2 * d * C + 2 * d + 1);
+  auto put = [&](int i, float v) { pwb[i] = accumulate ? pwb[i] + v : v; };
   for (int idx = tid; idx < d * C; idx += nt) {
     const int j = idx / C, c = idx % C;
-    pwb[idx] = gqp[j] * xbar[c];
+    put(idx, gqp[j] * xbar[c]);
     float s = 0.f;
     for (int i = 0; i < k; ++i) s = fmaf(gL[i], S[i * C + c], s);
-    pwb[d * C + d + idx] = qp[j] * s * invHW;
+    put(d * C + d + idx, qp[j] * s * invHW);
   }
   for (int j = tid; j < d; j += nt) {
-    pwb[d * C + j] = gqp[j];
+    put(d * C + j, gqp[j]);
     float s = 0.f;
     for (int i = 0; i < k; ++i) s += gL[i] * (float)(rhi[i] - rlo[i]);
-    pwb[2 * d * C + d + j] = qp[j] * s * (float)W * invHW;
+    put(2 * d * C + d + j, qp[j] * s * (float)W * invHW);
   }
-  if (tid == 0) pwb[2 * d * C + 2 * d] = s_gtau;
+  if (tid == 0) put(2 * d * C + 2 * d, s_gtau);
   __syncthreads();
   // additive row term of dL/dx: (Wq^T gqp)[c]/HW + wkq[c]/HW * sum_{i: y in rows_i} gL_i
   for (int idx = tid; idx < C * H; idx += nt) {
@@ -345,16 +347,23 @@ size_t attn_bwd_scratch_bytes(const gnca_model& m, int B, int H, int nparts) {
          al256((size_t)B * (2 * m.d_model * m.C + 2 * m.d_model + 1) * 4);
 }
 
+// defer_reduce: the per-sample parameter gradients are ACCUMULATED in sc.pw (zeroed by the caller before the first step)
+// and run_attn_param_reduce adds them to gparams once, after the last step of a BPTT
 int run_attn_bwd(const gnca_model& m, const Packed& P, const float* packed, const StepArgs& a, const float* rowsum,
-                 const AttnBwdScratch& sc, int nparts, float* gparams, cudaStream_t st) {
+                 const AttnBwdScratch& sc, int nparts, float* gparams, cudaStream_t st, bool defer_reduce) {
   const int C = m.C, d = m.d_model, k = a.k;
   const int stage = (size_t)C * a.H * 4 <= 32 * 1024;
   const size_t smem = (size_t)(4 * C + 2 * d + k * C + k * d + 3 * k) * 4 + 2 * k * 4 + (size_t)2 * d * (C + 1) * 4 + (stage ? (size_t)C * a.H * 4 : 0) + 64;
   if (smem > 48 * 1024)
     GNCA_CHECK_CUDA(cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_attn_bwd<<<a.B, 128, smem, st>>>(a, P, C, d, packed, rowsum, sc.gw_part, nparts, sc.grow, sc.pw, stage);
+  k_attn_bwd<<<a.B, 128, smem, st>>>(a, P, C, d, packed, rowsum, sc.gw_part, nparts, sc.grow, sc.pw, stage, defer_reduce ? 1 : 0);
   GNCA_LAUNCH_CHECK();
-  k_attn_param_reduce<<<4, 256, 0, st>>>(a.B, C, d, make_layout(m), sc.pw, gparams);
+  if (!defer_reduce) return run_attn_param_reduce(m, a.B, sc, gparams, st);
+  return 0;
+}
+
+int run_attn_param_reduce(const gnca_model& m, int B, const AttnBwdScratch& sc, float* gparams, cudaStream_t st) {
+  k_attn_param_reduce<<<4, 256, 0, st>>>(B, m.C, m.d_model, make_layout(m), sc.pw, gparams);
   GNCA_LAUNCH_CHECK();
   return 0;
 }
@@ -400,7 +409,7 @@ static int launch_graph_bwd(const gnca_model& m, const Packed& P, const float* p
   k_graph_wpart_reduce<<<2, 256, 0, st>>>(a.B * nblk, C, make_layout(m), wpart, gparams);
   GNCA_LAUNCH_CHECK();
   if (zp) {
-    int rc = run_attn_bwd(m, P, packed, a, ws.rowsum, sc, nblk, gparams, st);
+    int rc = run_attn_bwd(m, P, packed, a, ws.rowsum, sc, nblk, gparams, st, false);
     if (rc) return rc;
   }
   dim3 g2((HW + 255) / 256, a.B);

@@ -40,7 +40,8 @@ struct AttnBwdScratch {
 size_t attn_bwd_scratch_bytes(const gnca_model& m, int B, int H, int nparts);
 AttnBwdScratch carve_attn_bwd(void* base, const gnca_model& m, int B, int H, int nparts);
 int run_attn_bwd(const gnca_model& m, const Packed& P, const float* packed, const StepArgs& a, const float* rowsum,
-                 const AttnBwdScratch& sc, int nparts, float* gparams, cudaStream_t st);
+                 const AttnBwdScratch& sc, int nparts, float* gparams, cudaStream_t st, bool defer_reduce);
+int run_attn_param_reduce(const gnca_model& m, int B, const AttnBwdScratch& sc, float* gparams, cudaStream_t st);
 
 size_t graph_workspace_bytes(const gnca_model& m, int B, int H, int W);
 size_t bwd_workspace_bytes(const gnca_model& m, int B, int H, int W);
