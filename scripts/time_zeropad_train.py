@@ -10,7 +10,7 @@ from graph_neural_cellular_automata_b200.training.trainer import GraphNCATrainer
 lib = _lib.load()
 target = torch.from_numpy(np.load(os.path.join(ROOT, "tests/golden/target_gecko_surrogate.npy"))).cuda()
 QUICK = bool(os.environ.get("ZP_ONLY"))          # under ncu: the zero-pad model only, few iterations
-for zp in ((True,) if QUICK else (False, True)):
+for zp in ((os.environ["ZP_ONLY"] != "torus",) if QUICK else (False, True)):     # ZP_ONLY=torus: the torus model only
     torch.manual_seed(1234); random.seed(1234)
     m = G.NeuralCAGraph(16, update_hidden=128, img_size=40, update_gain=0.05, alpha_thr=0.12, message_gain=0.25, hidden_only=True,
                         graph_zero_padded_shift=zp)
