@@ -196,3 +196,12 @@ def test_reference_staging_recipe():
     with torch.no_grad():
         y = model(bench_ref.make_seed(2, "cpu"), fire_rate=0.5)
     assert tuple(y.shape) == (2, 16, 40, 40) and bool(torch.isfinite(y).all())
+
+
+def test_history_allocation_is_quantised_in_steps():
+    """rollout.py sizes the BPTT record buffer / dense history for T rounded up to 64 steps, so that rollouts of slightly
+    different lengths reuse one cached block (a fresh 29 GB cudaMalloc per new maximum cost 70 ms in the long regime)."""
+    from graph_neural_cellular_automata_b200.rollout import _round_up_steps, _QUANT_SLACK_BYTES
+    assert [_round_up_steps(t) for t in (0, 1, 16, 17, 64, 65, 79, 80, 128, 390, 400)] == \
+           [0, 1, 16, 64, 64, 128, 128, 128, 128, 448, 448]
+    assert _QUANT_SLACK_BYTES >= 1 << 30
