@@ -123,11 +123,16 @@ __global__ void __launch_bounds__(kBThreads) k_bwd_norm(BwdArgs A, Packed P, con
     A.postmask[(size_t)b * HW + cell] = post ? 1 : 0;
     const float* go = A.gout + (size_t)b * C * HW + cell;
     float s1 = 0.f, s2 = 0.f;
+    // all loads of the cell before the first use (one L2 round trip instead of one per channel: the conditional u load
+    // made every channel its own basic block); u of an inactive cell is read and dropped
+    float gv[C], uv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { gv[c] = go[(size_t)c * HW]; uv[c] = ub[(size_t)c * HW + cell]; }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      float g = go[(size_t)c * HW];
+      float g = gv[c];
       if (c == 3 && !post) g = 0.f;
-      const float uu = act ? ub[(size_t)c * HW + cell] : 0.f;
+      const float uu = act ? uv[c] : 0.f;
       const float th = act ? tanhf(fmaf(uu, s_sc[c], s_bi[c])) : s_idle_th[c];
       const float gz = g * a.update_gain * (1.f - th * th);
       if (act) A.gz[((size_t)b * C + c) * HW + cell] = gz;
