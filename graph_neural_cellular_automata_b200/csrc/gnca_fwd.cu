@@ -230,13 +230,27 @@ __global__ void __launch_bounds__(kThreads) k_compact(StepArgs a, int C, uint16_
   const int cell0 = chunk * CH;
   uint32_t bal[kPerWarp / 32];
   int n = 0;
+  // the 3x3 alpha windows of all the thread's cells are requested before the first use, from clamped coordinates (a
+  // duplicated tap never changes a maximum): one L2 round trip instead of one per cell and edge test
+  float win[kPerWarp / 32][9];
+#pragma unroll
+  for (int it = 0; it < kPerWarp / 32; ++it) {
+    const int cell = min(cell0 + warp * kPerWarp + it * 32 + lane, HW - 1);
+    const int y = cell / W, x = cell - y * W;
+    const int ru = (y > 0 ? y - 1 : y) * W, rc = y * W, rd = (y < H - 1 ? y + 1 : y) * W;
+    const int xl = x > 0 ? x - 1 : x, xr = x < W - 1 ? x + 1 : x;
+    win[it][0] = __ldg(alpha + ru + xl); win[it][1] = __ldg(alpha + ru + x); win[it][2] = __ldg(alpha + ru + xr);
+    win[it][3] = __ldg(alpha + rc + xl); win[it][4] = __ldg(alpha + rc + x); win[it][5] = __ldg(alpha + rc + xr);
+    win[it][6] = __ldg(alpha + rd + xl); win[it][7] = __ldg(alpha + rd + x); win[it][8] = __ldg(alpha + rd + xr);
+  }
 #pragma unroll
   for (int it = 0; it < kPerWarp / 32; ++it) {
     const int cell = cell0 + warp * kPerWarp + it * 32 + lane;
     bool act = false, sal = false;
     if (cell < HW) {
-      const int y = cell / W, x = cell - y * W;
-      const float mx = alive_max(alpha, y, x, H, W);          // one window maximum serves both thresholds
+      float mx = win[it][0];
+#pragma unroll
+      for (int q = 1; q < 9; ++q) mx = fmaxf(mx, win[it][q]);   // one window maximum serves both thresholds
       act = mx > a.alpha_thr && fires(a, fr, b, cell);
       sal = mx > a.graph_alpha_thr;
     }
