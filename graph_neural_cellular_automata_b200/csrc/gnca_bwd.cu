@@ -213,7 +213,8 @@ struct BwdSmem {
 // Accumulation into a partial that ONE thread owns (this block's weight-gradient slot / this chunk's dL/dw slot): a
 // reduction without return value instead of load - add - store.  The thread does not wait for the L2 round trip (the
 // read-modify-writes of a batch held 18 % of the kernel's stall samples and the block barrier behind them another 19 %),
-// and the result is the same sequence of fp32 additions: operations of one thread on one address stay in program order.
+// and the result is the same sequence of fp32 additions: operations of one thread on one address stay in program order
+// (the instruction is REDG.E.ADD.F32.FTZ.RN: round to nearest like the FADD it replaces; subnormal sums flush to zero).
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
